@@ -1,0 +1,142 @@
+/*
+ * pypde_b200 — C ABI of the sm_100a kernels behind pypde's Chebyshev
+ * spectral-Galerkin time-step hot path.
+ *
+ * This is the drop-in boundary: every entry point replaces one call the
+ * reference makes into its f2py Fortran modules / scipy.fftpack / scipy.sparse
+ * (file:line given per function, relative to the reference root).
+ *
+ * Conventions
+ *   - all data are float64 DEVICE pointers owned by the caller (no ownership
+ *     transfer); 2-D arrays are row-major (n0, n1) with a leading dimension
+ *     `ld*` counted in elements (>= n1); 1-D data is a (n, 1) array;
+ *   - `axis` = 0: the operator acts along axis 0 (one independent problem per
+ *     column), `axis` = 1: along axis 1 (one problem per row); `batch` is the
+ *     extent of the other axis;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *   - every function returns 0 on success; on failure a non-zero code, and
+ *     pde_last_error() holds the message (thread-local);
+ *   - small coefficient tables (diagonals, stencils) are DEVICE pointers too,
+ *     uploaded once by the host-side plan objects; opaque plan handles own
+ *     only their constant tables.
+ *   - nothing here falls back to the CPU: without a CUDA device every compute
+ *     entry point fails with PDE_ERR_CUDA.
+ */
+#ifndef PYPDE_B200_H
+#define PYPDE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDE_OK 0
+#define PDE_ERR_ARG 1
+#define PDE_ERR_CUDA 2
+#define PDE_ERR_UNSUPPORTED 3
+
+/* ---- library ---------------------------------------------------------------- */
+const char *pde_last_error(void);
+int pde_version(void);
+/* SM count and compute capability of the current device. */
+int pde_device_info(int *sm_count, int *cc_major, int *cc_minor);
+/* Number of kernel launches issued by this library since the last reset
+ * (bench.py's `gpu_launches`). */
+long pde_launch_count(void);
+void pde_launch_count_reset(void);
+
+/* ---- DCT-I -------------------------------------------------------------------
+ * Replaces scipy.fftpack.dctn(f, type=1, axes=(0,)) (pypde/bases/chebyshev.py:85-93)
+ * and, with mode 1/2, the scale/sign/mass passes wrapped around it in
+ * Chebyshev.forward_fft (:67-76, :143-149) and Chebyshev.backward_fft (:78-83).
+ *   PDE_DCT_RAW : y_k = x_0 + (-1)^k x_{L-1} + 2 sum_{n=1}^{L-2} x_n cos(pi k n/(L-1))
+ *   PDE_DCT_FWD : physical values on the Gauss-Lobatto grid -> Chebyshev coefficients
+ *   PDE_DCT_BWD : Chebyshev coefficients -> physical values
+ * Input entries n_in..L-1 along the axis are taken as zero (zero_pad,
+ * pypde/bases/utils.py:89-110); only the first n_out outputs are written
+ * (zero_unpad, :113-115).
+ * algo: 0 = auto, 1 = dense cosine matrix (fp64 tensor-core GEMM),
+ *       2 = shared-memory FFT (L-1 even with factors 2,3,5 only), 3 = Bluestein. */
+#define PDE_DCT_RAW 0
+#define PDE_DCT_FWD 1
+#define PDE_DCT_BWD 2
+typedef struct pde_dct_plan_s *pde_dct_plan_t;
+int pde_dct_plan_create(pde_dct_plan_t *plan, int L, int algo);
+int pde_dct_plan_destroy(pde_dct_plan_t plan);
+int pde_dct_plan_algo(pde_dct_plan_t plan);
+int pde_dct1(pde_dct_plan_t plan, int mode, const double *x, long ldx, int n_in,
+             double *y, long ldy, int n_out, int batch, int axis, void *stream);
+
+/* ---- Galerkin stencil maps ----------------------------------------------------
+ * to_cheb: u = S v with S[k,k] = 1, S[k+2,k] = s[k]
+ *   (GalerkinChebyshev.to_chebyshev, chebyshev.py:287-293; stencils :382-392, :426-436).
+ *   v has M entries along the axis, u gets n_out >= 1 entries (entries beyond
+ *   M+1 are zero: Galerkin-space zero padding for dealiasing, field.py:48-51).
+ * from_cheb: v = (S^T S)^-1 S^T u, the S^T product followed by the offset-2
+ *   tridiagonal solve (chebyshev.py:295-337 -> tdma.f90:55-106).  Tables:
+ *   s[M], a[M-2] = sub-diagonal of S^T S, den[M], w[M-2] = Thomas denominators
+ *   and c/den ratios, computed on the host exactly as tdma.f90:82-89 does. */
+int pde_to_cheb(const double *s, const double *v, long ldv, int M,
+                double *u, long ldu, int n_out, int batch, int axis, void *stream);
+int pde_from_cheb(const double *s, const double *a, const double *den, const double *w,
+                  const double *u, long ldu, int M, double *v, long ldv,
+                  int batch, int axis, void *stream);
+/* tdma alone: solve_tdma_1d/2d(a,b,c,d,k=2) (bases/linalg/tdma.py:92-100). */
+int pde_tdma2_solve(const double *a, const double *den, const double *w,
+                    const double *d, long ldd, int n, double *x, long ldx,
+                    int batch, int axis, void *stream);
+
+/* ---- Chebyshev derivative recurrence -----------------------------------------
+ * differentiate_cheby.diff_1d/diff_2d (bases/fortran/differentiate_cheby.f90:1-53)
+ * applied `order` times, then divided by `div` (grad(): `dvhat /= scale**deriv`,
+ * field_operations.py:40-45; pass 1.0 for none).  c and dc are n long along the
+ * axis, dc[n-1] = 0.  c and dc must not alias. */
+int pde_cheb_diff(const double *c, long ldc, double *dc, long lddc, int n, int batch,
+                  int axis, int order, double div, void *stream);
+
+/* ---- banded matrix product ----------------------------------------------------
+ * y = A x (accumulate = 0) or y += A x (accumulate = 1) along the axis for an
+ * (n_out x n_in) matrix with `ndiag` diagonals: diags[d*n_out + r] = A[r, r+offsets[d]]
+ * (PlanRHS.solve with the banded B, B@S matrices: solver/plans.py:54-74,
+ * matrix.py:48-53).  offsets is a HOST array, ascending; products are summed
+ * in ascending column order like the CSR mat-vec. */
+int pde_banded_mul(const double *diags, const int *offsets, int ndiag,
+                   const double *x, long ldx, int n_in, double *y, long ldy, int n_out,
+                   int batch, int axis, int accumulate, void *stream);
+
+/* ---- banded solves (in place on x) -------------------------------------------
+ * fdma:   4 diagonals at offsets -2,0,2,4, pre-factored l,d,u1,u2 (Plan_fdma.FDMA_LU,
+ *         solver/plans.py:226-234) -> solve_fdma_1d/2d (solver/linalg/fortran/fdma.f90:1-98).
+ * twodma: diagonals 0,+2 -> solve_twodma_1d/2d (twodma.f90:1-61). */
+int pde_fdma_solve(const double *l, const double *d, const double *u1, const double *u2,
+                   double *x, long ldx, int n, int batch, int axis, void *stream);
+int pde_twodma_solve(const double *d, const double *u, double *x, long ldx, int n, int batch,
+                     int axis, void *stream);
+
+/* ---- eigen-diagonalised Poisson core -------------------------------------------
+ * solve_fdma_type2(A, C, lam, x, axis=0, singular) (fdma.f90:146-195 with
+ * init_fdma :102-143): for column i solve (A + lam_i C) x_i = b_i.
+ * The plan factors every column ONCE on the device (same operation order as
+ * init_fdma) and keeps the l,d,u1,u2 tables (4 n m doubles); the reference
+ * re-factors on every call.  Adiag/Cdiag: HOST arrays [4][n] holding the
+ * diagonals at offsets -2,0,2,4 (entry r = M[r, r+off], 0 outside); lam: HOST [m]. */
+typedef struct pde_poisson_plan_s *pde_poisson_plan_t;
+int pde_poisson_plan_create(pde_poisson_plan_t *plan, const double *Adiag, const double *Cdiag,
+                            const double *lam, int n, int m, int singular);
+int pde_poisson_plan_destroy(pde_poisson_plan_t plan);
+int pde_poisson_solve(pde_poisson_plan_t plan, double *x, long ldx, void *stream);
+
+/* ---- dense fp64 contraction -----------------------------------------------------
+ * C(m x n) = A(m x k) * B, B given as (k x n) [transB = 0] or (n x k) [transB = 1];
+ * PlanRHS / PlanLHS "multiply" with the dense Hy, Qy of the Poisson plan
+ * (templates/poisson.py:93-108): axis 0 -> C = Mat * X, axis 1 -> C = X * Mat^T. */
+int pde_gemm_f64(int transB, const double *A, long lda, const double *B, long ldb,
+                 double *C, long ldc, int m, int n, int k, void *stream);
+
+/* ---- layout helper ------------------------------------------------------------- */
+/* out(n1 x n0) = in(n0 x n1)^T */
+int pde_transpose(const double *in, long ldin, double *out, long ldout, int n0, int n1, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYPDE_B200_H */

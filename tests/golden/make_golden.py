@@ -162,15 +162,15 @@ def primitives():
         out["dct1_%d_y" % L] = Base(max(L, 2), "CH").dctn(x)
     # banded solvers
     n, m = 21, 6
+    A = np.zeros((n, n))
+    for off in (-2, 0, 2, 4):
+        A += np.diag(rng.standard_normal(n - abs(off)) + (5.0 if off == 0 else 0.0), off)
+    l, d, u1, u2 = P.fdma_lu(A)
+    d2, u = rng.standard_normal(n) + 3.0, rng.standard_normal(n - 2)
     for axis in (0, 1):
-        A = np.zeros((n, n))
-        for off in (-2, 0, 2, 4):
-            A += np.diag(rng.standard_normal(n - abs(off)) + (5.0 if off == 0 else 0.0), off)
-        l, d, u1, u2 = P.fdma_lu(A)
         b = rng.standard_normal((n, m) if axis == 0 else (m, n))
         x = K.solve_fdma_2d(l, d, u1, u2, np.asfortranarray(b.copy()), axis)
         out["fdma_A"], out["fdma_b%d" % axis], out["fdma_x%d" % axis] = A, b, np.ascontiguousarray(x)
-        d2, u = rng.standard_normal(n) + 3.0, rng.standard_normal(n - 2)
         x = K.solve_twodma_2d(d2, u, np.asfortranarray(b.copy()), axis)
         out["twodma_d"], out["twodma_u"], out["twodma_x%d" % axis] = d2, u, np.ascontiguousarray(x)
     return out

@@ -1,0 +1,142 @@
+"""CPU: the C-ABI library loads and exports every symbol include/pypde_b200.h declares
+(no compute calls without a GPU), plus the host-side setup logic of the product against
+the oracle (bit-identical setup tables)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from oracle import pypde_port as P
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, "include", "pypde_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(pde_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_header_symbols_exported():
+    from pypde_b200 import _cabi
+    lib = _cabi.lib()
+    names = _declared()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), "symbol %s declared in include/pypde_b200.h is not exported" % n
+    # every declared entry point has a ctypes prototype and vice versa
+    assert sorted(_cabi.SIGNATURES) == names
+
+
+def test_library_is_loud_without_gpu():
+    import torch
+    from pypde_b200 import _cabi
+    lib = _cabi.lib()
+    assert lib.pde_version() >= 100
+    if not torch.cuda.is_available():
+        assert lib.pde_device_info(None, None, None) != 0
+        assert b"CUDA" in lib.pde_last_error() or b"cuda" in lib.pde_last_error()
+        with pytest.raises(_cabi.PdeError):
+            _cabi.device()
+
+
+def test_no_oracle_import_in_product():
+    """The product path must never import the oracle (or any CPU fallback)."""
+    pkg = os.path.join(ROOT, "pypde_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(d, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(d, f)
+                assert "/root/reference" not in src, os.path.join(d, f)
+
+
+@pytest.mark.parametrize("kind", ["CD", "CN"])
+@pytest.mark.parametrize("N", [20, 64, 96, 257])
+def test_stencil_tables_bit_identical(kind, N):
+    from pypde_b200.bases import Base
+    b = Base(N, kind)
+    o = P.Basis(N, kind)
+    s = b.stencil_diag().copy()
+    s[np.abs(s) < 1e-12] = 0
+    assert np.array_equal(s, np.diag(o.S, -2))
+    l2, d, u2 = b._init_stencil_inv()
+    assert np.array_equal(l2, o.l2) and np.array_equal(d, o.d) and np.array_equal(u2, o.u2)
+    assert np.array_equal(b.x, o.x)
+    assert (b.S_sp != o.S_sp).nnz == 0
+
+
+@pytest.mark.parametrize("kinds", [("CD", "CN"), ("CN", "CN"), ("CD", "CD")])
+def test_solver_setup_bit_identical(kinds):
+    """Sparse O(N) assembly of the Helmholtz / Poisson matrices == the reference's dense assembly."""
+    from pypde_b200.bases import Base
+    from pypde_b200.solver.plans import Plan_fdma
+    from pypde_b200.templates.hholtz import _axis_matrices
+    from pypde_b200.solver.utils import eigdecomp
+    N, lam, scale = 40, 0.0137, (0.75, 0.5)
+    bases = [Base(N, k) for k in kinds]
+    obases = [P.Basis(N, k) for k in kinds]
+    oh = P.HelmholtzADI(obases, lam, scale)
+    for axis in (0, 1):
+        S, B, I = _axis_matrices(bases[axis])
+        A = B @ S - lam * (1.0 / scale[axis] ** 2.0) * I @ S
+        assert np.array_equal(B.toarray(), oh.rhs[axis].toarray())
+        assert np.array_equal((B @ S).toarray(), oh.old[axis].toarray())
+        l, d, u1, u2 = (np.asarray(A.diagonal(k)).copy() for k in (-2, 0, 2, 4))
+        Plan_fdma.FDMA_LU(l, d, u1, u2)
+        for mine, ref in zip((l, d, u1, u2), oh.lu[axis]):
+            assert np.array_equal(mine, ref)
+    op = P.PoissonEig(obases, singular=True, scale=scale)
+    Sx, Bx, Ix = _axis_matrices(bases[0])
+    assert np.array_equal((Ix @ Sx * (1.0 / scale[0] ** 2.0)).toarray(), op.Ax)
+    assert np.array_equal((Bx @ Sx).toarray(), op.Cx)
+    Sy, By, Iy = _axis_matrices(bases[1])
+    By = By.toarray()
+    Ay = (Iy @ Sy * (1.0 / scale[1] ** 2.0)).toarray()
+    Cy = np.asarray(By @ Sy)
+    CyI = np.linalg.inv(Cy)
+    wy, Qy, QyI = eigdecomp(CyI @ Ay)
+    wy[0] += 1e-20
+    assert np.array_equal(wy, op.wy) and np.array_equal(Qy, op.Qy)
+    assert np.array_equal(QyI @ CyI @ By, op.Hy)
+
+
+def test_pseudoinverse_matches_oracle():
+    from pypde_b200.bases.dmsuite import pseudoinverse_spectral, gauss_lobatto
+    for N in (12, 50):
+        assert np.array_equal(pseudoinverse_spectral(N, 2), P.pinv_d2(N))
+        assert np.array_equal(gauss_lobatto(N - 1), P.gauss_lobatto(N))
+
+
+def test_star_import_surface():
+    import pypde_b200
+    for name in ("np", "memoized", "Base", "Field", "FieldBC", "MultiField", "Integrator", "SolverPlan",
+                 "PlanRHS", "PlanLHS", "grad", "galerkin_to_cheby", "cheby_to_galerkin", "conv_term",
+                 "convective_term", "avg_x", "avg_vol", "interpolate", "initplot", "plot"):
+        assert hasattr(pypde_b200, name), name
+
+
+def test_integrator_cadence():
+    """iterate() stops at maxtime and saves every tsave (integrator.py:14-28)."""
+    from pypde_b200.solver.integrator import Integrator
+
+    class Dummy(Integrator):
+        def __init__(self):
+            Integrator.__init__(self)
+            self.dt, self.tsave, self.n, self.saves = 0.1, 0.5, 0, 0
+
+        def update(self):
+            self.n += 1
+
+        def update_time(self):
+            self.time += self.dt
+
+        def save(self):
+            self.saves += 1
+
+    d = Dummy()
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        d.iterate(2.0)
+    assert d.n == 20 and d.saves == 4

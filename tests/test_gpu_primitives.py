@@ -1,0 +1,262 @@
+"""GPU parity tests: every C-ABI primitive (called through the reference-facing Python
+classes) against the golden fixtures and the CPU oracle on the same seeded inputs.
+
+Tolerances: recurrence / banded kernels are compiled without FMA contraction and must be
+BIT-EXACT; the DCT-I (different summation order than pocketfft) and the dense contractions
+must agree to <= 1e-13 relative (L2), well inside the 1e-12 budget of the north star."""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+DCT_TOL = 2e-14
+
+
+@pytest.fixture(scope="module")
+def dev():
+    import torch
+    assert torch.cuda.is_available()
+    return torch.device("cuda")
+
+
+def T(a, dev):
+    import torch
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=dev)
+
+
+def H(t):
+    return t.detach().cpu().numpy()
+
+
+def test_library_reports_blackwell():
+    from pypde_b200 import _cabi
+    import ctypes
+    sm, ma, mi = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _cabi.check(_cabi.lib().pde_device_info(ctypes.byref(sm), ctypes.byref(ma), ctypes.byref(mi)))
+    assert sm.value > 0 and ma.value >= 10, "built for sm_100a only"
+
+
+@pytest.mark.parametrize("N", [20, 33, 64])
+@pytest.mark.parametrize("kind", ["CH", "CD", "CN"])
+def test_basis_against_golden(golden_prim, dev, kind, N):
+    from pypde_b200 import Base
+    g = golden_prim
+    b = Base(N, kind)
+    key = "%s%d" % (kind, N)
+    f, c = T(g[key + "_f"], dev), T(g[key + "_c"], dev)
+    assert rel_l2(H(b.forward_fft(f)), g[key + "_forward"]) < DCT_TOL
+    assert rel_l2(H(b.backward_fft(c)), g[key + "_backward"]) < DCT_TOL
+    for order in (1, 2):
+        assert np.array_equal(H(b.derivative(c, order)), g[key + "_deriv%d" % order])
+    if kind != "CH":
+        assert np.array_equal(H(b.to_chebyshev(c)), g[key + "_to_cheb"])
+        assert np.array_equal(H(b.from_chebyshev(T(g[key + "_u"], dev))), g[key + "_from_cheb"])
+    # NumPy in -> NumPy out (drop-in behaviour of examples/transform1d.py)
+    out = b.forward_fft(g[key + "_f"])
+    assert isinstance(out, np.ndarray) and rel_l2(out, g[key + "_forward"]) < DCT_TOL
+
+
+@pytest.mark.parametrize("L", [2, 3, 5, 17, 64, 96, 128, 192, 257])
+def test_raw_dct1_against_scipy_golden(golden_prim, dev, L):
+    from pypde_b200 import ops
+    g = golden_prim
+    plan = ops.DctPlan.get(L)
+    y = ops.dct1(plan, ops.RAW, T(g["dct1_%d_x" % L], dev), axis=0)
+    assert rel_l2(H(y), g["dct1_%d_y" % L]) < DCT_TOL
+
+
+@pytest.mark.parametrize("axis", [0, 1])
+@pytest.mark.parametrize("kind", ["CH", "CD", "CN"])
+def test_axis1_equals_axis0_transposed(dev, kind, axis):
+    """axis-1 (row) kernels against the oracle applied to the transposed problem; ragged sizes."""
+    from pypde_b200 import Base
+    from oracle import pypde_port as P
+    rng = np.random.default_rng(11)
+    N, nb = 45, 37
+    b, o = Base(N, kind), P.Basis(N, kind)
+    shp = lambda n: (n, nb) if axis == 0 else (nb, n)
+    tr = (lambda a: a) if axis == 0 else (lambda a: a.T)
+    f, c, u = rng.standard_normal(shp(N)), rng.standard_normal(shp(b.M)), rng.standard_normal(shp(N))
+    assert rel_l2(H(b.forward_fft(T(f, dev), axis=axis)), tr(o.forward(tr(f)))) < DCT_TOL
+    assert rel_l2(H(b.backward_fft(T(c, dev), axis=axis)), tr(o.backward(tr(c).copy()))) < DCT_TOL
+    for order in (1, 2):
+        assert np.array_equal(H(b.derivative(T(c, dev), order, axis=axis, div=0.75 ** order)),
+                              tr(o.deriv(tr(c), order) / 0.75 ** order))
+    if kind != "CH":
+        assert np.array_equal(H(b.to_chebyshev(T(c, dev), axis=axis)), tr(o.to_cheb(tr(c))))
+        assert np.array_equal(H(b.from_chebyshev(T(u, dev), axis=axis)), tr(o.from_cheb(tr(u))))
+
+
+@pytest.mark.parametrize("axis", [0, 1])
+def test_banded_solvers_bit_exact(golden_prim, dev, axis):
+    from pypde_b200 import PlanLHS
+    g = golden_prim
+    b = g["fdma_b%d" % axis]
+    plan = PlanLHS(g["fdma_A"], ndim=2, axis=axis, method="fdma")
+    x = T(b, dev)
+    out = plan.solve(x)
+    assert out.data_ptr() == x.data_ptr(), "fdma solves in place like the reference"
+    assert np.array_equal(H(x), g["fdma_x%d" % axis])
+    A2 = np.diag(g["twodma_d"]) + np.diag(g["twodma_u"], 2)
+    x = PlanLHS(A2, ndim=2, axis=axis, method="twodma").solve(T(b, dev))
+    assert np.array_equal(H(x), g["twodma_x%d" % axis])
+    # 1-D
+    b1 = np.ascontiguousarray(b[:, 0] if axis == 0 else b[0, :])
+    x1 = PlanLHS(g["fdma_A"], ndim=1, axis=0, method="fdma").solve(T(b1, dev))
+    assert np.array_equal(H(x1), g["fdma_x%d" % axis][:, 0] if axis == 0 else g["fdma_x%d" % axis][0, :])
+    # numpy in -> solved in place on the caller's array
+    bn = b.copy()
+    plan.solve(bn)
+    assert np.array_equal(bn, g["fdma_x%d" % axis])
+
+
+@pytest.mark.parametrize("n,batch", [(5, 1), (6, 3), (64, 1000), (2046, 40), (3070, 9)])
+@pytest.mark.parametrize("axis", [0, 1])
+def test_fdma_sizes_vs_oracle(dev, n, batch, axis):
+    """Minimum, ragged and maximum (row-tile limit) sizes of the 4-diagonal solve."""
+    from pypde_b200 import ops, _cabi as C
+    from oracle import kernels as K, pypde_port as P
+    rng = np.random.default_rng(n * 7 + batch)
+    A = np.zeros((n, n))
+    for off in (-2, 0, 2, 4):
+        if n - abs(off) > 0:
+            A += np.diag(rng.standard_normal(n - abs(off)) * 0.3 + (3.0 if off == 0 else 0.0), off)
+    l, d, u1, u2 = P.fdma_lu(A)
+    b = rng.standard_normal((n, batch) if axis == 0 else (batch, n))
+    ref = K.solve_fdma_2d(l, d, u1, u2, b.copy(), axis)
+    tabs = [C.upload(t if t.size else np.zeros(1)) for t in (l, d, u1, u2)]
+    x = ops.fdma_solve(*tabs, T(b, dev), axis=axis)
+    assert np.array_equal(H(x), ref)
+
+
+def test_banded_product_and_dense_product(dev):
+    from pypde_b200 import PlanRHS
+    import scipy.sparse as sp
+    rng = np.random.default_rng(2)
+    n_out, n_in, nb = 38, 40, 17
+    A = sp.diags([rng.standard_normal(n_out), rng.standard_normal(n_out), rng.standard_normal(n_out - 2)],
+                 [0, 2, 4], shape=(n_out, n_in), format="csr")
+    for axis in (0, 1):
+        b = rng.standard_normal((n_in, nb) if axis == 0 else (nb, n_in))
+        ref = A @ b if axis == 0 else (A @ b.T).T
+        assert np.array_equal(H(PlanRHS(A, ndim=2, axis=axis).solve(T(b, dev))), ref)
+        D = rng.standard_normal((n_out, n_in))          # dense -> tensor-core contraction
+        ref = D @ b if axis == 0 else b @ D.T
+        assert rel_l2(H(PlanRHS(D, ndim=2, axis=axis).solve(T(b, dev))), ref) < 1e-14
+
+
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (7, 5, 3), (128, 64, 16), (129, 65, 17), (300, 257, 511), (62, 62, 64)])
+@pytest.mark.parametrize("transB", [False, True])
+def test_gemm_f64(dev, m, n, k, transB):
+    import torch
+    from pypde_b200 import ops
+    rng = np.random.default_rng(m + n + k)
+    A = rng.standard_normal((m, k))
+    B = rng.standard_normal((n, k) if transB else (k, n))
+    ref = A @ (B.T if transB else B)
+    assert rel_l2(H(ops.gemm(T(A, dev), T(B, dev), transB)), ref) < 1e-14
+    # fp64 torch reference of the same op (cuBLAS)
+    tref = T(A, dev) @ (T(B, dev).T if transB else T(B, dev))
+    assert rel_l2(H(ops.gemm(T(A, dev), T(B, dev), transB)), H(tref)) < 1e-14
+
+
+def test_fields_against_golden(golden_fs, dev):
+    from pypde_b200 import Base, Field, FieldBC, grad, galerkin_to_cheby, cheby_to_galerkin
+    g = golden_fs
+    N0, N1 = 40, 20
+    for kx, ky in (("CD", "CN"), ("CH", "CH"), ("CN", "CD")):
+        fld = Field([Base(N0, kx, dealias=3 / 2), Base(N1, ky, dealias=3 / 2)])
+        key = "f2d_%s%s" % (kx, ky)
+        assert rel_l2(H(fld.forward(T(g[key + "_v"], dev))), g[key + "_fwd"]) < DCT_TOL
+        assert rel_l2(H(fld.backward(T(g[key + "_vhat"], dev))), g[key + "_bwd"]) < DCT_TOL
+        bwd = fld.dealias.backward(T(g[key + "_vhat"], dev))
+        assert tuple(bwd.shape) == (60, 30)
+        assert rel_l2(H(bwd), g[key + "_dbwd"]) < DCT_TOL
+        fwd = fld.dealias.forward(T(g[key + "_dbwd"] * g[key + "_dbwd"], dev))
+        assert tuple(fwd.shape) == tuple(g[key + "_dfwd"].shape)
+        assert rel_l2(H(fwd), g[key + "_dfwd"]) < 10 * DCT_TOL
+        fld.vhat = g[key + "_vhat"]
+        for deriv in ((1, 0), (0, 1), (2, 0), (1, 1)):
+            assert np.array_equal(H(grad(fld, deriv, scale=(0.75, 0.5))), g[key + "_grad%d%d" % deriv])
+        if kx != "CH":
+            assert np.array_equal(H(galerkin_to_cheby(T(g[key + "_vhat"], dev), fld)), g[key + "_g2c"])
+            assert np.array_equal(H(cheby_to_galerkin(T(g[key + "_cheb"], dev), fld)), g[key + "_c2g"])
+    for axis in (0, 1):
+        fb = FieldBC([Base(N0, "CD"), Base(N1, "CN")], axis=axis)
+        fb.add_bc(g["fbc%d_bc" % axis])
+        assert rel_l2(H(fb.v), g["fbc%d_v" % axis]) < DCT_TOL
+        assert rel_l2(H(fb.vhat), g["fbc%d_vhat" % axis]) < 10 * DCT_TOL
+
+
+def test_solver_templates_against_golden(golden_fs, dev):
+    from pypde_b200 import Base
+    from pypde_b200.templates.hholtz import solverplan_hholtz1d, solverplan_hholtz2d_adi
+    from pypde_b200.templates.poisson import solverplan_poisson1d, solverplan_poisson2d
+    g = golden_fs
+    N0, N1 = 50, 40
+    for kx, ky in (("CD", "CN"), ("CN", "CN"), ("CD", "CD")):
+        key = kx + ky
+        bases = [Base(N0, kx), Base(N1, ky)]
+        s = solverplan_hholtz2d_adi(bases, lam=0.013, scale=(0.75, 0.5))
+        r = s.solve_rhs(T(g["hh_" + key + "_rhs"], dev))
+        r += s.solve_old(T(g["hh_" + key + "_old"], dev))
+        assert np.array_equal(H(s.solve_lhs(r)), g["hh_" + key + "_x"]), "Helmholtz ADI is bit-exact"
+        p = solverplan_poisson2d(bases, singular=(key == "CNCN"), scale=(0.75, 0.5))
+        x = p.solve_lhs(p.solve_rhs(T(g["hh_" + key + "_rhs"], dev)))
+        assert rel_l2(H(x), g["po_" + key + "_x"]) < 1e-9      # golden from another host's LAPACK
+    f, uo = g["t1d_f"], g["t1d_old"]
+    for kind in ("CD", "CN"):
+        s = solverplan_hholtz1d([Base(50, kind)], lam=0.02)
+        r = s.solve_rhs(T(f, dev))
+        r += s.solve_old(T(uo, dev))
+        assert np.array_equal(H(s.solve_lhs(r)), g["hh1_%s_x" % kind])
+        p = solverplan_poisson1d([Base(50, kind)], singular=(kind == "CN"))
+        assert np.array_equal(H(p.solve_lhs(p.solve_rhs(T(f, dev)))), g["po1_%s_x" % kind])
+
+
+@pytest.mark.parametrize("kinds", [("CN", "CN"), ("CD", "CD")])
+def test_poisson_against_oracle_same_host(dev, kinds):
+    """Same-host comparison (identical LAPACK setup on both sides): tight tolerance."""
+    from pypde_b200 import Base
+    from pypde_b200.templates.poisson import solverplan_poisson2d
+    from oracle import pypde_port as P
+    rng = np.random.default_rng(4)
+    N0, N1 = 66, 50
+    rhs = rng.standard_normal((N0, N1))
+    sing = kinds == ("CN", "CN")
+    o = P.PoissonEig([P.Basis(N0, kinds[0]), P.Basis(N1, kinds[1])], singular=sing, scale=(0.5, 0.5))
+    ref = o.solve_lhs(o.solve_rhs(rhs))
+    p = solverplan_poisson2d([Base(N0, kinds[0]), Base(N1, kinds[1])], singular=sing, scale=(0.5, 0.5))
+    x = p.solve_lhs(p.solve_rhs(T(rhs, dev)))
+    assert rel_l2(H(x), ref) < 1e-12
+
+
+def test_poisson_analytic(dev):
+    """reference test/test_poisson2d.py: cos(pi x/2) cos(pi y/2) forcing, rtol 1e-3."""
+    from pypde_b200 import Base, Field
+    from pypde_b200.templates.poisson import solverplan_poisson2d
+    N0, N1 = 50, 40
+    fld = Field([Base(N0, "CD"), Base(N1, "CD")])
+    xx, yy = np.meshgrid(fld.x, fld.y, indexing="ij")
+    arg = np.pi / 2
+    sol = np.cos(arg * xx) * np.cos(arg * yy)
+    f = -2 * arg ** 2 * sol
+    ch = Field([Base(N0, "CH"), Base(N1, "CH")])
+    fhat = ch.forward(T(f, dev))
+    p = solverplan_poisson2d(fld.xs, singular=False)
+    fld.vhat = p.solve_lhs(p.solve_rhs(fhat))
+    fld.backward()
+    assert np.allclose(H(fld.v), sol, rtol=1e-3, atol=1e-6)
+
+
+def test_transform_roundtrip_large(dev):
+    """Size-independent property at transform-sweep sizes: backward(forward(f)) == f."""
+    import torch
+    from pypde_b200 import Base
+    for N, nb in ((512, 300), (1024, 64)):
+        b = Base(N, "CH")
+        f = torch.randn((N, nb), dtype=torch.float64, device=dev, generator=torch.Generator(dev).manual_seed(0))
+        back = b.backward_fft(b.forward_fft(f))
+        assert float(torch.linalg.norm(back - f) / torch.linalg.norm(f)) < 1e-13
