@@ -1,0 +1,414 @@
+#!/usr/bin/env python
+"""
+bench.py - headline benchmark of pypde_b200 (contract: see README / DESIGN.md §measurement).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload rbc2048|rbc512|rbc64]
+    python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
+
+Metric (BASELINE.json): RBC2D fp64 timesteps/sec at N x N.  A "step" is one full IMEX RK3 time
+step (3 stages: transforms, nonlinear terms, Helmholtz/Poisson solves) of
+navier.rbc2d.NavierStokes on synthetic initial fields.  One JSON line is printed by rank 0.
+
+  value      steps/s, state resident in HBM, CUDA-event timed, max over ranks
+  e2e        steps/s through the reference-facing API with HOST buffers: every step uploads the
+             state (T, U, V, pres coefficients) from pinned host memory, steps, and reads it back
+  roofline   dominant kernel of the step, timed live with CUDA events in an instrumented step
+  cpu_baseline  the CPU oracle (bit-identical port of the reference) on a bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (NavierStokes kwargs, description)
+    "rbc2048": dict(case="rbc", shape=(2048, 2048), ra=1e10, pr=1.0, dt=1e-4, tsave=None, dealias=True,
+                    integrator="rk3", beta=1.0, aspect=1.0),
+    "rbc512": dict(case="rbc", shape=(512, 512), ra=1e8, pr=1.0, dt=1e-3, tsave=None, dealias=True,
+                   integrator="rk3", beta=1.0, aspect=1.0),
+    "rbc64": dict(case="rbc", shape=(64, 64), ra=1e5, pr=1.0, dt=0.01, tsave=None, dealias=True,
+                  integrator="rk3", beta=1.0, aspect=1.0),
+}
+METRIC = "rbc2d_fp64_timesteps_per_sec"
+UNIT = "steps/s"
+
+
+def init_state(ns, shape, port=False):
+    """Synthetic initial fields of SURVEY.md §8(d).1 (same seed as the golden fixtures)."""
+    ns.set_velocity(m=1, n=1, amplitude=0.2)
+    ns.set_temperature(amplitude=0.2)
+    k0, k1 = min(16, shape[0] - 2), min(16, shape[1] - 2)
+    pert = 1e-3 * np.random.default_rng(0).standard_normal((k0, k1))
+    if port:
+        ns.That_[:k0, :k1] += pert
+    else:
+        import torch
+        ns.T.vhat[:k0, :k1] += torch.as_tensor(pert, device=ns.T.vhat.device)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- CPU arms
+def cpu_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count()
+
+
+def oracle_sample(cfg, full_steps):
+    """Times the CPU oracle (bit-identical port of the reference's NumPy/SciPy/Fortran path).
+    full_steps > 0: that many complete RK3 steps.  full_steps == 0: ONLY the first RK3 stage of
+    one step (bounded sample); the step rate is extrapolated with the reference's own primitive
+    count per stage (22 : 40 : 40 1-D transforms)."""
+    from oracle import pypde_port as P
+    t0 = time.perf_counter()
+    o = P.RBC2D(**cfg)
+    init_state(o, cfg["shape"], port=True)
+    setup = time.perf_counter() - t0
+    if full_steps > 0:
+        t0 = time.perf_counter()
+        for _ in range(full_steps):
+            o.update()
+        dt = (time.perf_counter() - t0) / full_steps
+        return 1.0 / dt, setup, "%d full RK3 step(s) of %dx%d" % (full_steps, *cfg["shape"])
+    saved = o.nstage
+    o.nstage = 1                       # run stage 1 only (a, b, c of RK3 stage 1)
+    t0 = time.perf_counter()
+    o.update()
+    dt = time.perf_counter() - t0
+    o.nstage = saved
+    factor = 102.0 / 22.0 if cfg["integrator"] == "rk3" else 1.0
+    return 1.0 / (dt * factor), setup, ("stage 1 of one RK3 step of %dx%d (%.1f s), step time = stage-1 time x %.2f "
+                                        "(reference's 1-D transform count per stage 22:40:40)"
+                                        % (*cfg["shape"], dt, factor))
+
+
+def run_reference(args, cfg):
+    """--impl reference: the reference's CPU path.  /root/reference does not exist on the GPU box
+    and its Fortran cannot be built (no gfortran): the oracle port stands in (kind = "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    budget = float(os.environ.get("PDE_BENCH_CPU_BUDGET_S", "150"))
+    from oracle import pypde_port as P
+    o = P.RBC2D(**cfg)
+    init_state(o, cfg["shape"], port=True)
+    # warm-up + cost probe: stage 1 of one step (22 of the 102 1-D transforms of an RK3 step)
+    nst = o.nstage
+    o.nstage = 1
+    t0 = time.perf_counter()
+    o.update()
+    probe = (time.perf_counter() - t0) * (102.0 / 22.0 if nst == 3 else 1.0)
+    o.nstage = nst
+    warm = 1
+    steps = max(1, min(args.steps, int(budget / max(probe, 1e-9))))
+    while warm < args.warmup and probe * (warm + steps) < budget:
+        o.update()
+        warm += 1
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        o.update()
+    dt = (time.perf_counter() - t0) / steps
+    val = 1.0 / dt
+    sample = "%d full RK3 step(s) of %dx%d after %d warm-up (requested %d/%d, clamped to a %.0f s budget)" % (
+        steps, *cfg["shape"], warm, args.steps, args.warmup, budget)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "shape": list(cfg["shape"]), "integrator": cfg["integrator"],
+                   "dealias": cfg["dealias"], "ra": cfg["ra"], "dt": cfg["dt"]},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cpu_cores(), "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- GPU arm
+class OpTimer:
+    """CUDA-event timer around every C-ABI call (instrumented step only)."""
+
+    def __init__(self):
+        self.records = []
+
+    def install(self):
+        import torch
+        from pypde_b200 import _cabi
+        lib = _cabi.lib()
+        self._orig = {}
+        for name in _cabi.SIGNATURES:
+            if name in ("pde_last_error", "pde_version", "pde_device_info", "pde_launch_count",
+                        "pde_launch_count_reset") or "plan" in name and "solve" not in name:
+                continue
+            fn = getattr(lib, name)
+            self._orig[name] = fn
+
+            def wrapped(*a, _fn=fn, _name=name):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                rc = _fn(*a)
+                e1.record()
+                self.records.append((_name, a, e0, e1))
+                return rc
+
+            setattr(lib, name, wrapped)
+
+    def remove(self):
+        from pypde_b200 import _cabi
+        for name, fn in self._orig.items():
+            setattr(_cabi.lib(), name, fn)
+
+    def summary(self):
+        out = {}
+        for name, a, e0, e1 in self.records:
+            key = name
+            work = None
+            if name == "pde_gemm_f64":
+                m, n, k = a[7], a[8], a[9]
+                key = "pde_gemm_f64"
+                work = 2.0 * m * n * k
+            d = out.setdefault(key, {"ms": 0.0, "launches": 0, "flop": 0.0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["launches"] += 1
+            if work:
+                d["flop"] += work
+        return out
+
+
+def fp64_peak_tflops():
+    """cuBLAS DGEMM 8192^3 (MEASURED_PEAKS.json has no fp64 entry, measure it)."""
+    import torch
+    n = 8192
+    a = torch.randn((n, n), dtype=torch.float64, device="cuda")
+    b = torch.randn((n, n), dtype=torch.float64, device="cuda")
+    best = 1e9
+    for i in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        if i:
+            best = min(best, e0.elapsed_time(e1))
+    del a, b
+    torch.cuda.empty_cache()
+    return 2.0 * n ** 3 / (best * 1e-3) / 1e12
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "MEASURED_PEAKS.json"
+    return {"hbm_gbs": 6650.0}, "fallback of B200_PROFILING.md"
+
+
+def run_gpu(args, cfg):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        raise SystemExit("bench.py: slab-sharded multi-GPU stepping is not implemented yet in this round "
+                         "(DESIGN.md §multi-GPU); run with --gpus 1")
+    torch.cuda.set_device(local)
+    from pypde_b200 import _cabi
+    from pypde_b200.navier import rbc2d
+
+    t0 = time.perf_counter()
+    ns = rbc2d.NavierStokes(**cfg)
+    init_state(ns, cfg["shape"])
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t0
+
+    fields = [ns.T, ns.U, ns.V, ns.pres]
+    for _ in range(args.warmup):
+        ns.update()
+        ns.update_time()
+    torch.cuda.synchronize()
+
+    # ---- device-resident timing -------------------------------------------------------
+    sampler = ClockSampler(local)
+    sampler.start()
+    _cabi.launch_count_reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        ns.update()
+        ns.update_time()
+    e1.record()
+    torch.cuda.synchronize()
+    launches = _cabi.launch_count()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    finite = bool(torch.isfinite(ns.T.vhat).all())
+
+    # ---- end-to-end: host buffers in, host buffers out, every step -----------------------
+    host_in = [torch.empty(f.vhat.shape, dtype=torch.float64).pin_memory() for f in fields]
+    host_out = [torch.empty(f.vhat.shape, dtype=torch.float64).pin_memory() for f in fields]
+    for h, f in zip(host_in, fields):
+        h.copy_(f.vhat)
+    h2d = sum(h.numel() * 8 for h in host_in)
+    d2h = sum(h.numel() * 8 for h in host_out)
+    e2e_steps = max(1, min(args.steps, 5))
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(e2e_steps):
+        for h, f in zip(host_in, fields):
+            f.vhat.copy_(h, non_blocking=True)
+        ns.update()
+        ns.update_time()
+        for h, f in zip(host_out, fields):
+            h.copy_(f.vhat, non_blocking=True)
+        torch.cuda.synchronize()
+        for hi, ho in zip(host_in, host_out):
+            hi.copy_(ho)
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+
+    # ---- instrumented step: per-kernel CUDA-event times, dominant kernel's roofline ----
+    timer = OpTimer()
+    timer.install()
+    ns.update()
+    torch.cuda.synchronize()
+    timer.remove()
+    ops_ms = timer.summary()
+    step_ms_instr = sum(v["ms"] for v in ops_ms.values())
+    top = max(ops_ms, key=lambda k: ops_ms[k]["ms"])
+    peaks, peak_src = measured_peaks()
+    fp64_peak = fp64_peak_tflops()
+    if top == "pde_gemm_f64":
+        t = ops_ms[top]
+        achieved = t["flop"] / (t["ms"] * 1e-3) / 1e12
+        roof = {"kernel": "k_gemm_f64 (DMMA; dense DCT-I + Poisson projections)", "bound": "tensor",
+                "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                "traffic": None, "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (fp64 tensor pipe; "
+                "MEASURED_PEAKS.json records no fp64 figure)",
+                "launches_per_step": t["launches"], "avg_launch_ms": t["ms"] / t["launches"],
+                "share_of_step": t["ms"] / step_ms_instr}
+    else:
+        t = ops_ms[top]
+        roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
+                "frac": None, "traffic": None, "peak_source": peak_src, "launches_per_step": t["launches"],
+                "avg_launch_ms": t["ms"] / t["launches"], "share_of_step": t["ms"] / step_ms_instr}
+
+    # ---- CPU baseline: bounded sample of the same workload on rank 0 -----------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        big = cfg["shape"][0] * cfg["shape"][1] > 600 * 600
+        v, cpu_setup, sample = oracle_sample(cfg, 0 if big else 2)
+        cpu = {"value": v, "unit": UNIT, "cores": cpu_cores(), "kind": "port", "sample": sample,
+               "setup_s": cpu_setup}
+
+    N = cfg["shape"][0]
+    D = int(N * 1.5)
+    M = N - 2
+    stage_bytes = 8 * (31 * M * M + 18 * M * N + 5 * N * N + 12 * D * M + 6 * D * N + D * D)
+    stage_flop = 2.0 * M * N * M + 2.0 * M ** 3
+    nst = ns.nstage
+    line = {
+        "metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "shape": list(cfg["shape"]), "integrator": cfg["integrator"],
+                   "dealias": cfg["dealias"], "ra": cfg["ra"], "dt": cfg["dt"], "stages_per_step": nst,
+                   "l2": "state + work arrays exceed the 126 MB L2 (no flush needed)" if N >= 1024
+                   else "working set fits L2 (small-grid regime, by design of the workload)",
+                   "finite": finite, "setup_s": setup_s},
+        "clocks": clocks,
+        "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "step_model": {"algorithmic_bytes_per_step": stage_bytes * nst, "dense_flop_per_step": stage_flop * nst,
+                       "hbm_fraction": (stage_bytes * nst / (peaks.get("hbm_gbs", 6650.0) * 1e9)) / (ms / args.steps * 1e-3),
+                       "combined_fraction": (stage_bytes * nst / (peaks.get("hbm_gbs", 6650.0) * 1e9)
+                                             + stage_flop * nst / (fp64_peak * 1e12)) / (ms / args.steps * 1e-3),
+                       "fp64_peak_tflops": fp64_peak, "hbm_peak_gbs": peaks.get("hbm_gbs")},
+        "kernel_ms_per_step": {k: round(v["ms"], 4) for k, v in sorted(ops_ms.items(), key=lambda kv: -kv[1]["ms"])},
+        "cpu_baseline": cpu,
+    }
+    if rank == 0:
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="rbc2048", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    cfg = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, cfg)
+    else:
+        run_gpu(args, cfg)
+
+
+if __name__ == "__main__":
+    main()

@@ -292,8 +292,8 @@ class _BoundaryBasis(GalerkinChebyshev):
         n = self.N if n_out is None else n_out
         u = torch.zeros((n,) + tuple(v.shape[1:]), dtype=torch.float64, device=v.device)
         S = self.coeff
-        u[0] = S[0, 0] * v[0] + S[0, 1] * v[1]
-        u[1] = S[1, 0] * v[0] + S[1, 1] * v[1]
+        u[0] = S[0][0] * v[0] + S[0][1] * v[1]
+        u[1] = S[1][0] * v[0] + S[1][1] * v[1]
         return u.movedim(0, axis).contiguous()
 
     @_io
