@@ -14,6 +14,46 @@ from .memoize import memoized
 
 SPARSE = True
 
+# Size policy of the dealiased twin space (MetaBase.create_dealiased_base):
+#   "reference": int(N * dealias) points, exactly like the reference (spectralbase.py:94-96)
+#   "fft":       the next L >= int(N * dealias) with L - 1 = 2^a 3^b 5^c even, so the
+#                dealiased DCT-I runs as a shared-memory FFT.  With the 3/2-rule the
+#                truncated coefficients of a product are alias-free for ANY grid of at
+#                least 3N/2 points, so both policies give the same time step up to
+#                rounding (tests/test_oracle_cpu.py::test_dealias_is_alias_free).
+DEALIAS_POLICY = "reference"
+
+
+def fft_friendly_size(n):
+    """Smallest L >= n such that L - 1 is even with prime factors 2, 3, 5 only."""
+    L = max(int(n), 3)
+    while True:
+        P = L - 1
+        if P % 2 == 0:
+            m = P
+            for f in (2, 3, 5):
+                while m % f == 0:
+                    m //= f
+            if m == 1:
+                return L
+        L += 1
+
+
+class dealias_policy:
+    """Context manager: `with dealias_policy("fft"): Field([Base(N, "CD", dealias=3/2), ...])`."""
+
+    def __init__(self, policy):
+        assert policy in ("reference", "fft")
+        self.policy = policy
+
+    def __enter__(self):
+        global DEALIAS_POLICY
+        self.saved, DEALIAS_POLICY = DEALIAS_POLICY, self.policy
+
+    def __exit__(self, *exc):
+        global DEALIAS_POLICY
+        DEALIAS_POLICY = self.saved
+
 
 def Base(N, key, *args, **kwargs):
     """Initialise a basis from its key ("CH", "CD", "CN", "DC", "NC" or the class names)."""
@@ -67,7 +107,10 @@ class MetaBase:
 
     def create_dealiased_base(self, size):
         """Twin space of int(size) points for dealiased transforms (spectralbase.py:94-96)."""
-        self.dealias = self.__class__(int(size), dealias=None)
+        size = int(size)
+        if DEALIAS_POLICY == "fft":
+            size = fft_friendly_size(size)
+        self.dealias = self.__class__(size, dealias=None)
 
     # -- stencil matrices on request ------------------------------------------------
     @property

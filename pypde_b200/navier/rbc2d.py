@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from .. import _cabi as C
-from ..bases.spectralbase import Base
+from ..bases.spectralbase import Base, dealias_policy
 from ..field import Field, FieldBC, MultiField
 from ..field_operations import cheby_to_galerkin, convective_term, galerkin_to_cheby
 from ..solver.integrator import Integrator
@@ -35,10 +35,18 @@ class NavierStokes(NavierStokesBase, Integrator):
 
     avail_cases = ["rbc", "linear", "zero"]
 
-    def __init__(self, case="rbc", **kwargs):
+    def __init__(self, case="rbc", dealias_grid="fft", **kwargs):
+        """dealias_grid: "fft" (default) evaluates the 3/2-rule products on the next
+        FFT-friendly Gauss-Lobatto grid >= 3N/2 (same truncated coefficients up to rounding);
+        "reference" uses exactly int(3N/2) points like the reference."""
         if case not in self.avail_cases:
             raise ValueError("Specified case is not available: ", self.avail_cases)
         self.case = case
+        self.dealias_grid = dealias_grid
+        with dealias_policy(dealias_grid):
+            self._construct(**kwargs)
+
+    def _construct(self, **kwargs):
         NavierStokesBase.__init__(self, **kwargs)
         Integrator.__init__(self)
 

@@ -260,3 +260,49 @@ def test_transform_roundtrip_large(dev):
         f = torch.randn((N, nb), dtype=torch.float64, device=dev, generator=torch.Generator(dev).manual_seed(0))
         back = b.backward_fft(b.forward_fft(f))
         assert float(torch.linalg.norm(back - f) / torch.linalg.norm(f)) < 1e-13
+
+
+@pytest.mark.parametrize("L", [3, 5, 7, 13, 17, 97, 129, 161, 193, 769, 1537, 3073])
+@pytest.mark.parametrize("axis", [0, 1])
+def test_fft_dct_vs_oracle(dev, L, axis):
+    """Shared-memory FFT DCT-I (algo 2) against scipy's pocketfft through the oracle, all three
+    modes, with zero padding (n_in < L) and truncation (n_out < L); ragged batch sizes."""
+    from pypde_b200 import ops
+    from oracle import pypde_port as P
+    rng = np.random.default_rng(L)
+    plan = ops.DctPlan(L, algo=2)
+    assert plan.algo == 2
+    nb = 37 if L < 1000 else 11
+    o = P.Basis(L, "CH")
+    tr = (lambda a: a) if axis == 0 else (lambda a: np.ascontiguousarray(a.T))
+    x = rng.standard_normal((L, nb))
+    from scipy.fftpack import dctn
+    tol = 5e-15 * max(1.0, np.log2(L))
+    got = ops.dct1(plan, ops.RAW, T(tr(x), dev), axis=axis)
+    assert rel_l2(tr(H(got)), dctn(x, type=1, axes=(0,))) < tol
+    got = ops.dct1(plan, ops.FWD, T(tr(x), dev), axis=axis)
+    assert rel_l2(tr(H(got)), o.forward(x)) < tol
+    got = ops.dct1(plan, ops.BWD, T(tr(x), dev), axis=axis)
+    assert rel_l2(tr(H(got)), o.backward(x.copy())) < tol
+    if L >= 7:
+        n_in, n_out = (2 * L) // 3, (2 * L) // 3 + 1
+        xp = np.zeros((L, nb))
+        xp[:n_in] = x[:n_in]
+        got = ops.dct1(plan, ops.BWD, T(tr(x[:n_in]), dev), axis=axis)
+        assert rel_l2(tr(H(got)), o.backward(xp.copy())) < tol
+        got = ops.dct1(plan, ops.FWD, T(tr(x), dev), axis=axis, n_out=n_out)
+        assert tuple(tr(H(got)).shape) == (n_out, nb)
+        assert rel_l2(tr(H(got)), o.forward(x)[:n_out]) < tol
+
+
+def test_fft_dct_roundtrip_full_size(dev):
+    """BASELINE-size property: backward(forward(f)) == f on the 3073-point dealias grid."""
+    import torch
+    from pypde_b200 import ops
+    plan = ops.DctPlan.get(3073)
+    assert plan.algo == 2
+    f = torch.randn((3073, 2048), dtype=torch.float64, device=dev, generator=torch.Generator(dev).manual_seed(1))
+    for axis in (0, 1):
+        g = f if axis == 0 else f.T.contiguous()
+        back = ops.dct1(plan, ops.BWD, ops.dct1(plan, ops.FWD, g, axis=axis), axis=axis)
+        assert float(torch.linalg.norm(back - g) / torch.linalg.norm(g)) < 1e-14

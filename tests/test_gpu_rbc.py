@@ -34,10 +34,10 @@ def _pert(cfg):
     return k0, k1, 1e-3 * np.random.default_rng(0).standard_normal((k0, k1))
 
 
-def make(cfg):
+def make(cfg, **kw):
     import torch
     from pypde_b200.navier import rbc2d
-    ns = rbc2d.NavierStokes(**cfg)
+    ns = rbc2d.NavierStokes(**cfg, **kw)
     ns.set_velocity(m=1, n=1, amplitude=0.2)
     ns.set_temperature(amplitude=0.2)
     k0, k1, pert = _pert(cfg)
@@ -109,6 +109,20 @@ def test_rbc_step_parity(name, snaps):
         assert abs(nu - nu_o[0]) <= bound * abs(nu_o[0]), ("Nu (CUDA diagnostic)", nu, nu_o[0], bound)
         assert abs(nuv - nu_o[1]) <= bound * max(1.0, abs(nu_o[1]))
     assert abs(ns.time - snaps[-1] * ns.dt) < 1e-12
+
+
+def test_reference_dealias_grid_also_matches():
+    """dealias_grid="reference" (exactly int(3N/2) points, dense DCT) and the default FFT-friendly
+    grid agree with the oracle and with each other."""
+    cfg = _cases()["rbc64_rk3_dealias"]
+    a, b, o = make(cfg, dealias_grid="reference"), make(cfg), make_oracle(cfg)
+    assert tuple(a.U.dealias.shape_physical) == (96, 96) and tuple(b.U.dealias.shape_physical) == (97, 97)
+    for _ in range(5):
+        a.update()
+        b.update()
+        o.update()
+    for x, y, r in ((a.T.vhat, b.T.vhat, o.That_), (a.U.vhat, b.U.vhat, o.Uhat), (a.pres.vhat, b.pres.vhat, o.pres)):
+        assert rel_l2(H(x), r) < TOL and rel_l2(H(y), r) < TOL
 
 
 def test_nusselt_diagnostic_conditioning():
