@@ -5,217 +5,13 @@
 // either), so these kernels are BIT-IDENTICAL to the CPU oracle.  They are
 // latency / HBM bound, so the missing FMAs cost nothing.
 //
-// All sequential operators decouple into an even and an odd index chain
-// (offset-2 couplings only), so the unit of work is one (problem, parity) chain:
-//   axis 0: one thread per (column, parity); lanes run over consecutive columns,
-//           so every global access is a coalesced row segment;
-//   axis 1: a CTA stages R full rows in shared memory with coalesced loads
-//           (row pitch odd -> conflict-free), 2R threads sweep, coalesced store.
+// The sequential operators run as sequence-per-thread sweeps with a cp.async prefetch
+// ring (sweeps.cuh); this file holds the pointwise stencils, the Poisson LU set-up,
+// the transpose and the C-ABI entry points.
 #include "common.cuh"
+#include "sweeps.cuh"
 
 namespace pde {
-
-struct Acc {            // strided view of one problem
-    double *p;
-    long s;
-    __device__ __forceinline__ double ld(int i) const { return p[(long)i * s]; }
-    __device__ __forceinline__ void st(int i, double v) const { p[(long)i * s] = v; }
-};
-
-// ---------------------------------------------------------------------------
-// chain operators
-// ---------------------------------------------------------------------------
-
-// differentiate_cheby.f90:28-53.  dc[n-1] = 0 (f2py zero fill), dc[n-2] = 2(n-1)c[n-1],
-// dc[k] = dc[k+2] + 2(k+1)c[k+1] (k = n-3..1), dc[0] = dc[2]/2 + c[1].
-// The stored value is dc/div (grad()'s `dvhat /= scale**deriv`), the recurrence
-// runs on the undivided value.
-struct DiffOp {
-    int n;
-    double div;
-    int use_div;
-    static constexpr bool in_place = false;
-    __device__ __forceinline__ int n_in() const { return n; }
-    __device__ __forceinline__ int n_out() const { return n; }
-    __device__ void chain(Acc c, Acc dc, int p) const
-    {
-        int k = ((n - 1 - p) & 1) ? n - 2 : n - 1;   // largest index of parity p
-        if (k < 0) return;
-        double cur;
-        if (k == n - 1) cur = 0.0;
-        else cur = (double)(2 * (n - 1)) * c.ld(n - 1);
-        dc.st(k, use_div ? cur / div : cur);
-        for (k -= 2; k >= 1; k -= 2) {
-            cur = cur + (double)(2 * (k + 1)) * c.ld(k + 1);
-            dc.st(k, use_div ? cur / div : cur);
-        }
-        if (p == 0 && n >= 3) {
-            cur = cur / 2.0 + c.ld(1);
-            dc.st(0, use_div ? cur / div : cur);
-        }
-    }
-};
-
-// tdma.f90:55-106 with k = 2 and host-precomputed den / w (tdma.f90:82-89).
-// Optional fused S^T product in front (chebyshev.py:327): d_k = u_k + s_k u_{k+2}.
-struct TdmaOp {
-    int n;                 // number of unknowns (M)
-    const double *s;       // stencil sub-diagonal (nullptr: plain tdma, input has n entries)
-    const double *a, *den, *w;
-    static constexpr bool in_place = false;
-    __device__ __forceinline__ int n_in() const { return s ? n + 2 : n; }
-    __device__ __forceinline__ int n_out() const { return n; }
-    __device__ __forceinline__ double rhs(const Acc &u, int i) const
-    {
-        if (!s) return u.ld(i);
-        return u.ld(i) + __ldg(s + i) * u.ld(i + 2);
-    }
-    __device__ void chain(Acc u, Acc x, int p) const
-    {
-        if (p >= n) return;
-        int i = p;
-        double g = rhs(u, i) / __ldg(den + i);
-        x.st(i, g);
-        for (i += 2; i < n; i += 2) {
-            g = (rhs(u, i) - __ldg(a + i - 2) * g) / __ldg(den + i);
-            x.st(i, g);
-        }
-        i -= 2;                     // top of the chain: x = g
-        double xv = g;
-        for (i -= 2; i >= 0; i -= 2) {
-            xv = x.ld(i) - __ldg(w + i) * xv;
-            x.st(i, xv);
-        }
-    }
-};
-
-// fdma.f90:26-36 / :68-80
-struct FdmaOp {
-    int n;
-    const double *l, *d, *u1, *u2;
-    static constexpr bool in_place = true;
-    __device__ __forceinline__ int n_in() const { return n; }
-    __device__ __forceinline__ int n_out() const { return n; }
-    __device__ void chain(Acc x, Acc, int p) const
-    {
-        if (p >= n) return;
-        int i = p;
-        double prev = x.ld(i);
-        for (i += 2; i < n; i += 2) {
-            prev = x.ld(i) - __ldg(l + i - 2) * prev;
-            x.st(i, prev);
-        }
-        i -= 2;                      // top index of this parity (n-1 or n-2)
-        double x2 = prev / __ldg(d + i);
-        x.st(i, x2);
-        i -= 2;
-        if (i < 0) return;
-        double x4 = x2;
-        x2 = (x.ld(i) - __ldg(u1 + i) * x4) / __ldg(d + i);
-        x.st(i, x2);
-        for (i -= 2; i >= 0; i -= 2) {
-            double v = (x.ld(i) - __ldg(u1 + i) * x2 - __ldg(u2 + i) * x4) / __ldg(d + i);
-            x.st(i, v);
-            x4 = x2;
-            x2 = v;
-        }
-    }
-};
-
-// twodma.f90:17-22 / :45-58
-struct TwodmaOp {
-    int n;
-    const double *d, *u;
-    static constexpr bool in_place = true;
-    __device__ __forceinline__ int n_in() const { return n; }
-    __device__ __forceinline__ int n_out() const { return n; }
-    __device__ void chain(Acc x, Acc, int p) const
-    {
-        int i = ((n - 1 - p) & 1) ? n - 2 : n - 1;
-        if (i < 0) return;
-        double x2 = x.ld(i) / __ldg(d + i);
-        x.st(i, x2);
-        for (i -= 2; i >= 0; i -= 2) {
-            x2 = (x.ld(i) - __ldg(u + i) * x2) / __ldg(d + i);
-            x.st(i, x2);
-        }
-    }
-};
-
-// ---------------------------------------------------------------------------
-// drivers
-// ---------------------------------------------------------------------------
-template <class Op>
-__global__ void k_chain_cols(Op op, const double *in, long ldin, double *out, long ldout, int batch)
-{
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= batch) return;
-    op.chain(Acc{const_cast<double *>(in) + j, ldin}, Acc{out + j, ldout}, (int)threadIdx.y);
-}
-
-template <class Op>
-__global__ void k_chain_rows(Op op, const double *in, long ldin, double *out, long ldout,
-                             int nrows, int R, int W)
-{
-    extern __shared__ double sm[];
-    double *tin = sm;
-    double *tout = Op::in_place ? sm : sm + (long)R * W;
-    const int r0 = blockIdx.x * R;
-    const int rows = min(R, nrows - r0);
-    const int nin = op.n_in(), nout = op.n_out();
-    for (int r = 0; r < rows; ++r) {
-        const double *src = in + (long)(r0 + r) * ldin;
-        for (int i = threadIdx.x; i < nin; i += blockDim.x) tin[(long)r * W + i] = src[i];
-    }
-    __syncthreads();
-    if ((int)threadIdx.x < 2 * rows) {
-        const int r = threadIdx.x >> 1, p = threadIdx.x & 1;
-        op.chain(Acc{tin + (long)r * W, 1}, Acc{tout + (long)r * W, 1}, p);
-    }
-    __syncthreads();
-    for (int r = 0; r < rows; ++r) {
-        double *dst = out + (long)(r0 + r) * ldout;
-        for (int i = threadIdx.x; i < nout; i += blockDim.x) dst[i] = tout[(long)r * W + i];
-    }
-}
-
-template <class Op>
-static int launch_chain(const Op &op, const double *in, long ldin, double *out, long ldout,
-                        int batch, int axis, int nmax, cudaStream_t st, const char *what)
-{
-    if (batch <= 0 || nmax <= 0) return PDE_OK;
-    if (axis == 0) {
-        const int tx = batch >= 148 * 128 ? 128 : (batch >= 148 * 64 ? 64 : 32);
-        dim3 block(tx, 2);
-        k_chain_cols<Op><<<ceil_div(batch, tx), block, 0, st>>>(op, in, ldin, out, ldout, batch);
-        return after_launch(what);
-    }
-    const int W = nmax | 1;
-    const int tiles = Op::in_place ? 1 : 2;
-    const long budget = 200 * 1024;
-    int R = (int)(budget / ((long)tiles * W * 8));
-    if (R < 1) {
-        set_error("%s: axis-1 problem of length %d does not fit the shared-memory row tile", what, nmax);
-        return PDE_ERR_UNSUPPORTED;
-    }
-    // keep >= ~2 CTAs per SM when there are enough rows
-    const int want = ceil_div(batch, 2 * sm_count());
-    if (R > 32) R = 32;
-    if (R > want) R = want < 1 ? 1 : want;
-    const size_t smem = (size_t)tiles * R * W * 8;
-    static bool attr_done = false;   // one flag per Op instantiation
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(k_chain_rows<Op>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)budget + 8 * 1024);
-        if (e != cudaSuccess) {
-            set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(e));
-            return PDE_ERR_CUDA;
-        }
-        attr_done = true;
-    }
-    k_chain_rows<Op><<<ceil_div(batch, R), 128, smem, st>>>(op, in, ldin, out, ldout, batch, R, W);
-    return after_launch(what);
-}
 
 // ---------------------------------------------------------------------------
 // pointwise stencils: to_cheb and the banded product (no sequential coupling,
@@ -306,43 +102,6 @@ __global__ void k_poisson_factor(const double *__restrict__ Ad, const double *__
 #undef T
 }
 
-__global__ void k_poisson_solve(PoissonTables t, double *x, long ldx, int n, int m)
-{
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= m) return;
-    const int p = threadIdx.y;
-    const int off = t.off[j];
-    const int ne = n - off;
-    if (off && p == 0) x[j] = 0.0;                 // x(1,i) = 0.0
-    if (p >= ne) return;
-    double *xp = x + (long)off * ldx + j;
-    const long tb = (long)off * m + j;
-#define X(q) xp[(long)(q) * ldx]
-#define T(arr, q) arr[tb + (long)(q) * m]
-    int i = p;
-    double prev = X(i);
-    for (i += 2; i < ne; i += 2) {
-        prev = X(i) - T(t.l, i - 2) * prev;
-        X(i) = prev;
-    }
-    i -= 2;
-    double x2 = prev / T(t.d, i);
-    X(i) = x2;
-    i -= 2;
-    if (i < 0) return;
-    double x4 = x2;
-    x2 = (X(i) - T(t.u1, i) * x4) / T(t.d, i);
-    X(i) = x2;
-    for (i -= 2; i >= 0; i -= 2) {
-        const double v = (X(i) - T(t.u1, i) * x2 - T(t.u2, i) * x4) / T(t.d, i);
-        X(i) = v;
-        x4 = x2;
-        x2 = v;
-    }
-#undef X
-#undef T
-}
-
 // tiled transpose, 32x32 tiles, conflict-free
 __global__ void k_transpose(const double *__restrict__ in, long ldin, double *__restrict__ out, long ldout,
                             int n0, int n1)
@@ -368,6 +127,17 @@ using namespace pde;
 // ===========================================================================
 extern "C" {
 
+static SweepJob make_job(const double *in, long ldin, double *out, long ldout, int nseq)
+{
+    SweepJob j{};
+    j.in[0] = in;
+    j.ldin[0] = ldin;
+    j.out = out;
+    j.ldout = ldout;
+    j.nseq = nseq;
+    return j;
+}
+
 int pde_cheb_diff(const double *c, long ldc, double *dc, long lddc, int n, int batch, int axis,
                   int order, double div, void *stream)
 {
@@ -376,42 +146,67 @@ int pde_cheb_diff(const double *c, long ldc, double *dc, long lddc, int n, int b
     PDE_REQUIRE(order >= 1 && order <= 2, "order must be 1 or 2");
     PDE_REQUIRE(axis == 0 || axis == 1, "axis");
     cudaStream_t st = as_stream(stream);
+    SweepJobs jobs{};
+    jobs.njobs = 1;
+    jobs.n = n;
     if (order == 1) {
-        DiffOp op{n, div, div != 1.0};
-        return launch_chain(op, c, ldc, dc, lddc, batch, axis, n, st, "pde_cheb_diff");
+        jobs.j[0] = make_job(c, ldc, dc, lddc, batch);
+        jobs.j[0].flag = div != 1.0;
+        jobs.j[0].sc = div;
+        return launch_sweep<DiffDesc>(jobs, axis, st, "pde_cheb_diff");
     }
-    // order 2: c -> tmp -> dc
     double *tmp = nullptr;
     const long n0 = axis == 0 ? n : batch, n1 = axis == 0 ? batch : n;
     PDE_CUDA(cudaMallocAsync(&tmp, sizeof(double) * n0 * n1, st));
-    DiffOp op1{n, 1.0, 0};
-    int rc = launch_chain(op1, c, ldc, tmp, n1, batch, axis, n, st, "pde_cheb_diff(1/2)");
+    jobs.j[0] = make_job(c, ldc, tmp, n1, batch);
+    int rc = launch_sweep<DiffDesc>(jobs, axis, st, "pde_cheb_diff(1/2)");
     if (rc == PDE_OK) {
-        DiffOp op2{n, div, div != 1.0};
-        rc = launch_chain(op2, tmp, n1, dc, lddc, batch, axis, n, st, "pde_cheb_diff(2/2)");
+        jobs.j[0] = make_job(tmp, n1, dc, lddc, batch);
+        jobs.j[0].flag = div != 1.0;
+        jobs.j[0].sc = div;
+        rc = launch_sweep<DiffDesc>(jobs, axis, st, "pde_cheb_diff(2/2)");
     }
     cudaFreeAsync(tmp, st);
     return rc;
 }
 
+static int tdma_run(const double *s, const double *a, const double *den, const double *w, const double *u,
+                    long ldu, int n, double *x, long ldx, int batch, int axis, cudaStream_t st, const char *what)
+{
+    SweepJobs jobs{};
+    jobs.njobs = 1;
+    jobs.n = n;
+    jobs.j[0] = make_job(u, ldu, x, ldx, batch);
+    jobs.j[0].in[1] = s ? u : nullptr;
+    jobs.j[0].ldin[1] = ldu;
+    jobs.j[0].tab[0] = s;
+    jobs.j[0].tab[1] = a;
+    jobs.j[0].tab[2] = den;
+    jobs.j[0].tab[3] = w;
+    int rc = launch_sweep<TdmaFwd>(jobs, axis, st, what);
+    if (rc != PDE_OK) return rc;
+    jobs.j[0].in[0] = x;
+    jobs.j[0].ldin[0] = ldx;
+    jobs.j[0].in[1] = nullptr;
+    return launch_sweep<TdmaBwd>(jobs, axis, st, what);
+}
+
 int pde_tdma2_solve(const double *a, const double *den, const double *w, const double *d, long ldd,
                     int n, double *x, long ldx, int batch, int axis, void *stream)
 {
-    PDE_REQUIRE(a && den && w && d && x, "null pointer");
+    PDE_REQUIRE(a && den && w && d && x && d != x, "null/aliased pointer");
     PDE_REQUIRE(n >= 3, "n >= 3");
     PDE_REQUIRE(axis == 0 || axis == 1, "axis");
-    TdmaOp op{n, nullptr, a, den, w};
-    return launch_chain(op, d, ldd, x, ldx, batch, axis, n, as_stream(stream), "pde_tdma2_solve");
+    return tdma_run(nullptr, a, den, w, d, ldd, n, x, ldx, batch, axis, as_stream(stream), "pde_tdma2_solve");
 }
 
 int pde_from_cheb(const double *s, const double *a, const double *den, const double *w,
                   const double *u, long ldu, int M, double *v, long ldv, int batch, int axis, void *stream)
 {
-    PDE_REQUIRE(s && a && den && w && u && v, "null pointer");
+    PDE_REQUIRE(s && a && den && w && u && v && u != v, "null/aliased pointer");
     PDE_REQUIRE(M >= 3, "M >= 3");
     PDE_REQUIRE(axis == 0 || axis == 1, "axis");
-    TdmaOp op{M, s, a, den, w};
-    return launch_chain(op, u, ldu, v, ldv, batch, axis, M + 2, as_stream(stream), "pde_from_cheb");
+    return tdma_run(s, a, den, w, u, ldu, M, v, ldv, batch, axis, as_stream(stream), "pde_from_cheb");
 }
 
 int pde_fdma_solve(const double *l, const double *d, const double *u1, const double *u2, double *x,
@@ -420,8 +215,17 @@ int pde_fdma_solve(const double *l, const double *d, const double *u1, const dou
     PDE_REQUIRE(l && d && u1 && u2 && x, "null pointer");
     PDE_REQUIRE(n >= 5, "n >= 5");
     PDE_REQUIRE(axis == 0 || axis == 1, "axis");
-    FdmaOp op{n, l, d, u1, u2};
-    return launch_chain(op, x, ldx, x, ldx, batch, axis, n, as_stream(stream), "pde_fdma_solve");
+    SweepJobs jobs{};
+    jobs.njobs = 1;
+    jobs.n = n;
+    jobs.j[0] = make_job(x, ldx, x, ldx, batch);
+    jobs.j[0].tab[0] = l;
+    jobs.j[0].tab[1] = d;
+    jobs.j[0].tab[2] = u1;
+    jobs.j[0].tab[3] = u2;
+    int rc = launch_sweep<FdmaFwd>(jobs, axis, as_stream(stream), "pde_fdma_solve(fwd)");
+    if (rc != PDE_OK) return rc;
+    return launch_sweep<FdmaBwd>(jobs, axis, as_stream(stream), "pde_fdma_solve(bwd)");
 }
 
 int pde_twodma_solve(const double *d, const double *u, double *x, long ldx, int n, int batch, int axis,
@@ -430,8 +234,13 @@ int pde_twodma_solve(const double *d, const double *u, double *x, long ldx, int 
     PDE_REQUIRE(d && u && x, "null pointer");
     PDE_REQUIRE(n >= 3, "n >= 3");
     PDE_REQUIRE(axis == 0 || axis == 1, "axis");
-    TwodmaOp op{n, d, u};
-    return launch_chain(op, x, ldx, x, ldx, batch, axis, n, as_stream(stream), "pde_twodma_solve");
+    SweepJobs jobs{};
+    jobs.njobs = 1;
+    jobs.n = n;
+    jobs.j[0] = make_job(x, ldx, x, ldx, batch);
+    jobs.j[0].tab[0] = d;
+    jobs.j[0].tab[1] = u;
+    return launch_sweep<TwodmaBwd>(jobs, axis, as_stream(stream), "pde_twodma_solve");
 }
 
 int pde_to_cheb(const double *s, const double *v, long ldv, int M, double *u, long ldu, int n_out,
@@ -519,10 +328,20 @@ int pde_poisson_plan_destroy(pde_poisson_plan_t p)
 int pde_poisson_solve(pde_poisson_plan_t p, double *x, long ldx, void *stream)
 {
     PDE_REQUIRE(p && x, "null pointer");
-    const int tx = 32;
-    dim3 block(tx, 2);
-    k_poisson_solve<<<ceil_div(p->m, tx), block, 0, as_stream(stream)>>>(p->t, x, ldx, p->n, p->m);
-    return after_launch("pde_poisson_solve");
+    SweepJobs jobs{};
+    jobs.njobs = 1;
+    jobs.n = p->n;
+    jobs.j[0] = make_job(x, ldx, x, ldx, p->m);
+    jobs.j[0].itab = p->t.off;
+    jobs.j[0].in[1] = p->t.l;
+    jobs.j[0].ldin[1] = p->m;
+    int rc = launch_sweep<PoissonFwd>(jobs, 0, as_stream(stream), "pde_poisson_solve(fwd)");
+    if (rc != PDE_OK) return rc;
+    jobs.j[0].in[1] = p->t.d;
+    jobs.j[0].in[2] = p->t.u1;
+    jobs.j[0].in[3] = p->t.u2;
+    jobs.j[0].ldin[1] = jobs.j[0].ldin[2] = jobs.j[0].ldin[3] = p->m;
+    return launch_sweep<PoissonBwd>(jobs, 0, as_stream(stream), "pde_poisson_solve(bwd)");
 }
 
 int pde_transpose(const double *in, long ldin, double *out, long ldout, int n0, int n1, void *stream)

@@ -153,7 +153,7 @@ __device__ __forceinline__ double in_scale(int mode, int n, int P, double v)
 
 // AXIS = 1: sequence q is row q (contiguous); AXIS = 0: sequence q is column q (stride ld).
 template <int AXIS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 k_dct_fft(PassList pl, const double2 *__restrict__ W, const double2 *__restrict__ CS,
           const int *__restrict__ pos, int P, int mode, const double *__restrict__ x, long ldx, int n_in,
           double *__restrict__ y, long ldy, int n_out, int batch, int S)
@@ -228,11 +228,16 @@ static bool factor(int P, std::vector<int> &radices)
 {
     radices.clear();
     int n = P;
-    // odd radices first (large strides), then 4s, then a final 2
-    while (n % 5 == 0) { radices.push_back(5); n /= 5; }
+    // Power-of-two passes first (large strides: lanes read consecutive addresses), odd radices
+    // last: the final small-stride passes then step through shared memory with strides 3 / 5
+    // (co-prime to the 8 x 16-byte bank groups) instead of 4 / 16, which removes the 4-way bank
+    // conflicts ncu showed for a radix-4 tail (profiles/r01_dct_fft_v1.txt).
+    int n2 = 0;
+    while (n % 2 == 0) { ++n2; n /= 2; }
+    if (n2 & 1) radices.push_back(2);
+    for (int i = 0; i < n2 / 2; ++i) radices.push_back(4);
     while (n % 3 == 0) { radices.push_back(3); n /= 3; }
-    while (n % 4 == 0) { radices.push_back(4); n /= 4; }
-    while (n % 2 == 0) { radices.push_back(2); n /= 2; }
+    while (n % 5 == 0) { radices.push_back(5); n /= 5; }
     return n == 1;
 }
 
@@ -323,10 +328,13 @@ int fft_dct_exec(FftDctPlan *p, int mode, const double *x, long ldx, int n_in, d
     for (int i = 0; i < p->npass; ++i) pl.radix[i] = p->radix[i];
     const size_t smem = per_seq * S;
     const int grid = ceil_div(batch, S);
+    // >= 2 radix-4 butterflies per thread and pass; more warps hide the twiddle / smem latency
+    int T = 128;
+    while (T < 1024 && (long)T * 8 < (long)S * P) T <<= 1;
     if (axis == 1)
-        k_dct_fft<1><<<grid, 256, smem, st>>>(pl, p->W, p->CS, p->pos, P, mode, x, ldx, n_in, y, ldy, n_out, batch, S);
+        k_dct_fft<1><<<grid, T, smem, st>>>(pl, p->W, p->CS, p->pos, P, mode, x, ldx, n_in, y, ldy, n_out, batch, S);
     else
-        k_dct_fft<0><<<grid, 256, smem, st>>>(pl, p->W, p->CS, p->pos, P, mode, x, ldx, n_in, y, ldy, n_out, batch, S);
+        k_dct_fft<0><<<grid, T, smem, st>>>(pl, p->W, p->CS, p->pos, P, mode, x, ldx, n_in, y, ldy, n_out, batch, S);
     return after_launch("pde_dct1(fft)");
 }
 

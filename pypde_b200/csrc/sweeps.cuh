@@ -1,0 +1,454 @@
+// Sequence-per-thread sweep kernels with a cp.async prefetch ring (sm_100a).
+//
+// Every sequential operator of the Chebyshev-Galerkin path (derivative recurrence,
+// Thomas sweeps of the offset-2 tridiagonal and of the 4-diagonal systems) is one or
+// two monotone passes over independent sequences with O(1) state.  One THREAD owns one
+// sequence and walks it start to end (both parity chains interleaved -> ILP 2):
+//   LC ("lane-coalesced", axis 0): element i of sequence q at base[i*ld + q]; a warp
+//       touches one contiguous 256-byte row segment per step;
+//   TS ("thread-sequential", axis 1): element i of sequence q at base[q*ld + i]; every
+//       lane streams through its own row (32-byte sectors are reused over 4 steps via L1).
+// The recurrences are latency chains, so the only way to keep HBM busy is memory-level
+// parallelism: each thread keeps (SW_KC-1)*SW_C future elements of every input stream in
+// flight with 8-byte cp.async copies into its private shared-memory ring (no registers,
+// no barriers: a thread only ever reads what it copied itself); one group per chunk of
+// SW_C steps so the chain steps of a chunk run back to back.  Several arrays (e.g.
+// the U, V, T fields) are processed by one launch (blockIdx.y = job).
+//
+// Arithmetic is identical to the reference's Fortran, operation for operation (this
+// header is only included from translation units compiled with --fmad=false).
+#pragma once
+#include "common.cuh"
+#include <type_traits>
+
+namespace pde {
+
+constexpr int SW_C = 8;          // steps per chunk (one cp.async group)
+static_assert(true, "");
+constexpr int SW_KC = 4;         // chunks in the ring (SW_KC-1 chunks = 24 steps in flight per thread)
+constexpr int RING_K = SW_C * SW_KC;
+constexpr int SWEEP_MAX_JOBS = 8;
+constexpr int SWEEP_MAX_IN = 4;
+
+struct SweepJob {
+    const double *in[SWEEP_MAX_IN];
+    long ldin[SWEEP_MAX_IN];
+    double *out;
+    long ldout;
+    const double *tab[5];      // per-index coefficient tables (shared by all sequences)
+    const int *itab;           // per-sequence integer table (Poisson: singular offset)
+    int nseq;
+    int flag;
+    double sc;
+};
+
+struct SweepJobs {
+    int njobs;
+    int n;                     // sequence length (number of steps)
+    SweepJob j[SWEEP_MAX_JOBS];
+};
+
+__device__ __forceinline__ void cp_async_8(double *smem, const double *gmem)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+template <bool LC>
+struct Writer {
+    double *base;
+    long ld;
+    int q;
+    __device__ __forceinline__ void st(int i, double v) const
+    {
+        if (LC) base[(long)i * ld + q] = v;
+        else base[(long)q * ld + i] = v;
+    }
+};
+
+// Op interface:
+//   static constexpr int NIN;  static constexpr bool ASC;
+//   __device__ static int off(int s);                 index offset of stream s
+//   __device__ static int len(int s, int n, job);     valid index range [0, len) of stream s
+//   struct State;  __device__ static void init(State&, job, n, q);
+//   template <class W> __device__ static void step(State&, job, n, i, const double *v, W &out);
+template <class Op, bool LC, int BD>
+__global__ void __launch_bounds__(BD) k_sweep(SweepJobs jobs)
+{
+    extern __shared__ double ring[];
+    const SweepJob &job = jobs.j[blockIdx.y];
+    const int q = blockIdx.x * BD + threadIdx.x;
+    if (q >= job.nseq) return;
+    const int n = jobs.n;
+    double *my = ring + threadIdx.x;
+    constexpr int NIN = Op::NIN;
+    constexpr int K = RING_K;
+    constexpr int C = SW_C;
+    // this thread walks the chain of parity par: i = par, par+2, ... (ASC) or top, top-2, ... (DESC)
+    const int par = blockIdx.z;
+    const int np = (n - par + 1) / 2;                 // chain length
+    if (np <= 0) return;
+    const int top = par + 2 * (np - 1);
+
+    // per-stream base pointer of this sequence and element stride (in doubles)
+    const double *gq[NIN];
+    long es[NIN];
+    int slen[NIN];
+#pragma unroll
+    for (int s = 0; s < NIN; ++s) {
+        es[s] = LC ? job.ldin[s] : 1;
+        gq[s] = job.in[s] ? (LC ? job.in[s] + q : job.in[s] + (long)q * job.ldin[s]) : nullptr;
+        slen[s] = job.in[s] ? Op::len(s, n, job) : 0;
+    }
+    Writer<LC> out{job.out, job.ldout, q};
+
+    // generic (checked) chunk issue: steps c*C .. c*C+C-1 into ring chunk slot c % KC
+    auto issue_chunk = [&](int c) {
+#pragma unroll
+        for (int e = 0; e < C; ++e) {
+            const int t = c * C + e;
+            if (t >= np) break;
+            const int i = Op::ASC ? par + 2 * t : top - 2 * t;
+            const int slot = t & (K - 1);
+#pragma unroll
+            for (int s = 0; s < NIN; ++s) {
+                const int ii = i + Op::off(s);
+                if (ii >= 0 && ii < slen[s]) cp_async_8(my + (slot * NIN + s) * BD, gq[s] + (long)ii * es[s]);
+            }
+        }
+    };
+    // unchecked issue of a full interior chunk whose ring chunk slot CS is a compile-time constant
+    auto issue_fast = [&](int c, auto cs_tag) {
+        constexpr int CS = decltype(cs_tag)::value;
+        const int i0 = Op::ASC ? par + 2 * c * C : top - 2 * c * C;
+#pragma unroll
+        for (int s = 0; s < NIN; ++s) {
+            const long step = Op::ASC ? 2 * es[s] : -2 * es[s];
+            const double *g = gq[s] + (long)(i0 + Op::off(s)) * es[s];
+#pragma unroll
+            for (int e = 0; e < C; ++e) {
+                cp_async_8(my + ((CS * C + e) * NIN + s) * BD, g);
+                g += step;
+            }
+        }
+    };
+
+    typename Op::State st;
+    Op::init(st, job, n, q);
+    const int nchunks = (np + C - 1) / C;
+    // chunks [c_lo, c_hi) are "interior": full, every stream index valid, no edge logic in Op::step
+    // (all their steps satisfy 8 <= i <= n-9)
+    const int c_lo = 1;
+    const int c_hi = Op::ASC ? (n - 9 - par >= 0 ? ((n - 9 - par) / 2 + 1) / C : 0)
+                             : (top - 8 >= 0 ? ((top - 8) / 2 + 1) / C : 0);
+#pragma unroll 1
+    for (int c = 0; c < SW_KC - 1; ++c) {
+        if (c < nchunks) issue_chunk(c);
+        cp_async_commit_group();
+    }
+
+    auto generic_chunk = [&](int c) {
+        cp_async_wait_group<SW_KC - 2>();
+        double v[C][NIN];
+#pragma unroll
+        for (int e = 0; e < C; ++e) {
+            const int t = c * C + e;
+            const int i = Op::ASC ? par + 2 * t : top - 2 * t;
+            const int slot = t & (K - 1);
+#pragma unroll
+            for (int s = 0; s < NIN; ++s) {
+                const int ii = i + Op::off(s);
+                v[e][s] = (t < np && ii >= 0 && ii < slen[s]) ? my[(slot * NIN + s) * BD] : 0.0;
+            }
+        }
+        if (c + SW_KC - 1 < nchunks) issue_chunk(c + SW_KC - 1);
+        cp_async_commit_group();
+#pragma unroll
+        for (int e = 0; e < C; ++e) {
+            const int t = c * C + e;
+            if (t < np) Op::template step<false>(st, job, n, Op::ASC ? par + 2 * t : top - 2 * t, v[e], out);
+        }
+    };
+    auto fast_chunk = [&](int c, auto cs_tag) {
+        constexpr int CS = decltype(cs_tag)::value;                 // ring chunk slot of chunk c
+        constexpr int NS = (CS + SW_KC - 1) % SW_KC;                // slot of chunk c + KC - 1
+        cp_async_wait_group<SW_KC - 2>();
+        double v[C][NIN];
+#pragma unroll
+        for (int e = 0; e < C; ++e)
+#pragma unroll
+            for (int s = 0; s < NIN; ++s) v[e][s] = my[((CS * C + e) * NIN + s) * BD];
+        if (c + SW_KC - 1 < c_hi) issue_fast(c + SW_KC - 1, std::integral_constant<int, NS>{});
+        else if (c + SW_KC - 1 < nchunks) issue_chunk(c + SW_KC - 1);
+        cp_async_commit_group();
+        const int i0 = Op::ASC ? par + 2 * c * C : top - 2 * c * C;
+#pragma unroll
+        for (int e = 0; e < C; ++e) Op::template step<true>(st, job, n, Op::ASC ? i0 + 2 * e : i0 - 2 * e, v[e], out);
+    };
+
+    int c = 0;
+#pragma unroll 1
+    for (; c < nchunks && (c < c_lo || (c & (SW_KC - 1)) != 0); ++c) generic_chunk(c);
+    // steady state: SW_KC chunks per iteration so that ring offsets are compile-time constants
+#pragma unroll 1
+    for (; c + SW_KC <= c_hi; c += SW_KC) {
+        fast_chunk(c + 0, std::integral_constant<int, 0>{});
+        fast_chunk(c + 1, std::integral_constant<int, 1>{});
+        fast_chunk(c + 2, std::integral_constant<int, 2>{});
+        fast_chunk(c + 3, std::integral_constant<int, 3>{});
+    }
+#pragma unroll 1
+    for (; c < nchunks; ++c) generic_chunk(c);
+}
+
+// ---------------------------------------------------------------------------
+// operators
+// ---------------------------------------------------------------------------
+
+// differentiate_cheby.f90:28-53: dc[n-1] = 0, dc[n-2] = 2(n-1)c[n-1], dc[k] = dc[k+2] + 2(k+1)c[k+1],
+// dc[0] = dc[2]/2 + c[1]; stored value divided by job.sc when job.flag (grad(): /= scale**deriv).
+struct DiffDesc {
+    static constexpr int NIN = 1;
+    static constexpr bool ASC = false;
+    __device__ static int off(int) { return 0; }
+    __device__ static int len(int, int n, const SweepJob &) { return n; }
+    struct State {
+        double p0, p1;     // last dc of even / odd index
+    };
+    __device__ static void init(State &s, const SweepJob &, int, int) { s.p0 = s.p1 = 0.0; }
+    template <bool MID, class W>
+    __device__ static void step(State &s, const SweepJob &job, int n, int i, const double *v, W &out)
+    {
+        const int k = i - 1;
+        double cur;
+        if (MID) {
+            cur = ((k & 1) ? s.p1 : s.p0) + (double)(2 * i) * v[0];
+        } else {
+            if (i == n - 1) out.st(n - 1, 0.0);
+            if (i == 0) return;
+            if (i == n - 1) cur = (double)(2 * (n - 1)) * v[0];
+            else if (k >= 1) cur = ((k & 1) ? s.p1 : s.p0) + (double)(2 * i) * v[0];
+            else cur = s.p0 / 2.0 + v[0];
+        }
+        if (k & 1) s.p1 = cur;
+        else s.p0 = cur;
+        out.st(k, job.flag ? cur / job.sc : cur);
+    }
+};
+
+// tdma.f90:55-106, k = 2, forward part: g_i = (rhs_i - a_{i-2} g_{i-2}) / den_i with the fused
+// S^T product rhs_i = u_i + s_i u_{i+2} (chebyshev.py:327) when tab[0] = s is given.
+// tab: 0 = s (or null), 1 = a, 2 = den.
+struct TdmaFwd {
+    static constexpr int NIN = 2;
+    static constexpr bool ASC = true;
+    __device__ static int off(int s) { return s == 0 ? 0 : 2; }
+    __device__ static int len(int s, int n, const SweepJob &job)
+    {
+        if (s == 0) return n;
+        return job.tab[0] ? n + 2 : 0;
+    }
+    struct State {
+        double g0, g1;
+    };
+    __device__ static void init(State &s, const SweepJob &, int, int) { s.g0 = s.g1 = 0.0; }
+    template <bool MID, class W>
+    __device__ static void step(State &s, const SweepJob &job, int n, int i, const double *v, W &out)
+    {
+        double rhs = v[0];
+        if (job.tab[0]) rhs = v[0] + __ldg(job.tab[0] + i) * v[1];
+        double g;
+        if (!MID && i < 2) g = rhs / __ldg(job.tab[2] + i);
+        else g = (rhs - __ldg(job.tab[1] + i - 2) * ((i & 1) ? s.g1 : s.g0)) / __ldg(job.tab[2] + i);
+        if (i & 1) s.g1 = g;
+        else s.g0 = g;
+        out.st(i, g);
+    }
+};
+
+// back substitution x_i = g_i - w_i x_{i+2} (in place), tab[3] = w
+struct TdmaBwd {
+    static constexpr int NIN = 1;
+    static constexpr bool ASC = false;
+    __device__ static int off(int) { return 0; }
+    __device__ static int len(int, int n, const SweepJob &) { return n; }
+    struct State {
+        double x0, x1;
+    };
+    __device__ static void init(State &s, const SweepJob &, int, int) { s.x0 = s.x1 = 0.0; }
+    template <bool MID, class W>
+    __device__ static void step(State &s, const SweepJob &job, int n, int i, const double *v, W &out)
+    {
+        double x = v[0];
+        if (MID || i < n - 2) {
+            x = v[0] - __ldg(job.tab[3] + i) * ((i & 1) ? s.x1 : s.x0);
+            out.st(i, x);
+        }
+        if (i & 1) s.x1 = x;
+        else s.x0 = x;
+    }
+};
+
+// fdma.f90:26-36: forward x_i -= l_{i-2} x_{i-2}; tab: 0 = l, 1 = d, 2 = u1, 3 = u2
+struct FdmaFwd {
+    static constexpr int NIN = 1;
+    static constexpr bool ASC = true;
+    __device__ static int off(int) { return 0; }
+    __device__ static int len(int, int n, const SweepJob &) { return n; }
+    struct State {
+        double p0, p1;
+    };
+    __device__ static void init(State &s, const SweepJob &, int, int) { s.p0 = s.p1 = 0.0; }
+    template <bool MID, class W>
+    __device__ static void step(State &s, const SweepJob &job, int, int i, const double *v, W &out)
+    {
+        double x = v[0];
+        if (MID || i >= 2) {
+            x = v[0] - __ldg(job.tab[0] + i - 2) * ((i & 1) ? s.p1 : s.p0);
+            out.st(i, x);
+        }
+        if (i & 1) s.p1 = x;
+        else s.p0 = x;
+    }
+};
+
+struct FdmaBwd {
+    static constexpr int NIN = 1;
+    static constexpr bool ASC = false;
+    __device__ static int off(int) { return 0; }
+    __device__ static int len(int, int n, const SweepJob &) { return n; }
+    struct State {
+        double a2, a4, b2, b4;     // x_{i+2}, x_{i+4} of the even (a) / odd (b) chain
+    };
+    __device__ static void init(State &s, const SweepJob &, int, int) { s.a2 = s.a4 = s.b2 = s.b4 = 0.0; }
+    template <bool MID, class W>
+    __device__ static void step(State &s, const SweepJob &job, int n, int i, const double *v, W &out)
+    {
+        const double x2 = (i & 1) ? s.b2 : s.a2, x4 = (i & 1) ? s.b4 : s.a4;
+        const double d = __ldg(job.tab[1] + i);
+        double x;
+        if (!MID && i >= n - 2) x = v[0] / d;
+        else if (!MID && i >= n - 4) x = (v[0] - __ldg(job.tab[2] + i) * x2) / d;
+        else x = (v[0] - __ldg(job.tab[2] + i) * x2 - __ldg(job.tab[3] + i) * x4) / d;
+        out.st(i, x);
+        if (i & 1) {
+            s.b4 = s.b2;
+            s.b2 = x;
+        } else {
+            s.a4 = s.a2;
+            s.a2 = x;
+        }
+    }
+};
+
+// twodma.f90:17-22; tab: 0 = d, 1 = u
+struct TwodmaBwd {
+    static constexpr int NIN = 1;
+    static constexpr bool ASC = false;
+    __device__ static int off(int) { return 0; }
+    __device__ static int len(int, int n, const SweepJob &) { return n; }
+    struct State {
+        double x0, x1;
+    };
+    __device__ static void init(State &s, const SweepJob &, int, int) { s.x0 = s.x1 = 0.0; }
+    template <bool MID, class W>
+    __device__ static void step(State &s, const SweepJob &job, int n, int i, const double *v, W &out)
+    {
+        const double d = __ldg(job.tab[0] + i);
+        double x;
+        if (!MID && i >= n - 2) x = v[0] / d;
+        else x = (v[0] - __ldg(job.tab[1] + i) * ((i & 1) ? s.x1 : s.x0)) / d;
+        out.st(i, x);
+        if (i & 1) s.x1 = x;
+        else s.x0 = x;
+    }
+};
+
+// Poisson (A + lam_q C) columns with per-column LU tables (n x m arrays, same layout as x):
+// streams: 0 = x, 1 = L (read at i-2);  itab[q] = 1 where the singular branch drops row/col 0
+// (fdma.f90:173-185): that column's system starts at i = 1 and x[0] = 0.
+struct PoissonFwd {
+    static constexpr int NIN = 2;
+    static constexpr bool ASC = true;
+    __device__ static int off(int s) { return s == 0 ? 0 : -2; }
+    __device__ static int len(int, int n, const SweepJob &) { return n; }
+    struct State {
+        double p0, p1;
+        int off;
+    };
+    __device__ static void init(State &s, const SweepJob &job, int, int q)
+    {
+        s.p0 = s.p1 = 0.0;
+        s.off = job.itab[q];
+    }
+    template <bool MID, class W>
+    __device__ static void step(State &s, const SweepJob &, int, int i, const double *v, W &out)
+    {
+        if (!MID && i < s.off) {
+            out.st(i, 0.0);
+            return;
+        }
+        double x = v[0];
+        if (MID || i >= s.off + 2) {
+            x = v[0] - v[1] * ((i & 1) ? s.p1 : s.p0);
+            out.st(i, x);
+        }
+        if (i & 1) s.p1 = x;
+        else s.p0 = x;
+    }
+};
+
+// streams: 0 = x, 1 = D, 2 = U1, 3 = U2
+struct PoissonBwd {
+    static constexpr int NIN = 4;
+    static constexpr bool ASC = false;
+    __device__ static int off(int) { return 0; }
+    __device__ static int len(int, int n, const SweepJob &) { return n; }
+    struct State {
+        double a2, a4, b2, b4;
+        int off;
+    };
+    __device__ static void init(State &s, const SweepJob &job, int, int q)
+    {
+        s.a2 = s.a4 = s.b2 = s.b4 = 0.0;
+        s.off = job.itab[q];
+    }
+    template <bool MID, class W>
+    __device__ static void step(State &s, const SweepJob &, int n, int i, const double *v, W &out)
+    {
+        if (!MID && i < s.off) return;
+        const double x2 = (i & 1) ? s.b2 : s.a2, x4 = (i & 1) ? s.b4 : s.a4;
+        double x;
+        if (!MID && i >= n - 2) x = v[0] / v[1];
+        else if (!MID && i >= n - 4) x = (v[0] - v[2] * x2) / v[1];
+        else x = (v[0] - v[2] * x2 - v[3] * x4) / v[1];
+        out.st(i, x);
+        if (i & 1) {
+            s.b4 = s.b2;
+            s.b2 = x;
+        } else {
+            s.a4 = s.a2;
+            s.a2 = x;
+        }
+    }
+};
+
+template <class Op>
+static int launch_sweep(const SweepJobs &jobs, int axis, cudaStream_t st, const char *what)
+{
+    if (jobs.njobs <= 0 || jobs.n <= 0) return PDE_OK;
+    int maxseq = 0;
+    for (int j = 0; j < jobs.njobs; ++j) maxseq = jobs.j[j].nseq > maxseq ? jobs.j[j].nseq : maxseq;
+    if (maxseq <= 0) return PDE_OK;
+    constexpr int BD = 32;      // one warp per CTA: spreads the few thousand chains over all SMs
+    dim3 grid(ceil_div(maxseq, BD), jobs.njobs, 2);      // z = parity chain
+    const size_t smem = (size_t)RING_K * Op::NIN * BD * sizeof(double);
+    if (axis == 0) k_sweep<Op, true, BD><<<grid, BD, smem, st>>>(jobs);
+    else k_sweep<Op, false, BD><<<grid, BD, smem, st>>>(jobs);
+    return after_launch(what);
+}
+
+}  // namespace pde
