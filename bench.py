@@ -184,52 +184,44 @@ def run_reference(args, cfg):
 
 # --------------------------------------------------------------------------- GPU arm
 class OpTimer:
-    """CUDA-event timer around every C-ABI call (instrumented step only)."""
+    """CUDA-event timer around every C-ABI call of one (eager) time step: wraps the prebuilt launch
+    lists of the batched stepper."""
 
     def __init__(self):
         self.records = []
 
-    def install(self):
+    def run_step(self, ns):
         import torch
         from pypde_b200 import _cabi
-        lib = _cabi.lib()
-        self._orig = {}
-        for name in _cabi.SIGNATURES:
-            if name in ("pde_last_error", "pde_version", "pde_device_info", "pde_launch_count",
-                        "pde_launch_count_reset") or "plan" in name and "solve" not in name:
-                continue
-            fn = getattr(lib, name)
-            self._orig[name] = fn
-
-            def wrapped(*a, _fn=fn, _name=name):
+        fs = ns._fast
+        st = _cabi.stream()
+        for rk in range(ns.nstage):
+            for fn, args in fs.stage_calls[rk].calls:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                rc = _fn(*a)
+                _cabi.check(fn(*args, st))
                 e1.record()
-                self.records.append((_name, a, e0, e1))
-                return rc
-
-            setattr(lib, name, wrapped)
-
-    def remove(self):
-        from pypde_b200 import _cabi
-        for name, fn in self._orig.items():
-            setattr(_cabi.lib(), name, fn)
+                self.records.append((fn.__name__, args, e0, e1))
+        torch.cuda.synchronize()
 
     def summary(self):
         out = {}
         for name, a, e0, e1 in self.records:
             key = name
             work = None
+            if name == "pde_sweep":
+                key = "pde_sweep[%s,axis%d]" % (["diff", "tdma_fwd", "tdma_bwd", "fdma_fwd", "fdma_bwd", "twodma"][a[0]], a[1])
+            if name == "pde_dct1_multi":
+                key = "pde_dct1_multi[axis%d]" % a[10]
+                # algorithmic bytes: 8 read + 8 written per element of the longer side
+                work = 16.0 * a[2] * max(a[5], a[8]) * a[9]
             if name == "pde_gemm_f64":
-                m, n, k = a[7], a[8], a[9]
-                key = "pde_gemm_f64"
-                work = 2.0 * m * n * k
-            d = out.setdefault(key, {"ms": 0.0, "launches": 0, "flop": 0.0})
+                work = 2.0 * a[7] * a[8] * a[9]
+            d = out.setdefault(key, {"ms": 0.0, "launches": 0, "work": 0.0})
             d["ms"] += e0.elapsed_time(e1)
             d["launches"] += 1
             if work:
-                d["flop"] += work
+                d["work"] += work
         return out
 
 
@@ -275,7 +267,7 @@ def run_gpu(args, cfg):
     from pypde_b200.navier import rbc2d
 
     t0 = time.perf_counter()
-    ns = rbc2d.NavierStokes(**cfg)
+    ns = rbc2d.NavierStokes(graph=not args.no_graph, **cfg)
     init_state(ns, cfg["shape"])
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t0
@@ -329,29 +321,36 @@ def run_gpu(args, cfg):
 
     # ---- instrumented step: per-kernel CUDA-event times, dominant kernel's roofline ----
     timer = OpTimer()
-    timer.install()
-    ns.update()
-    torch.cuda.synchronize()
-    timer.remove()
+    _cabi.launch_count_reset()
+    timer.run_step(ns)
+    launches_per_step = _cabi.launch_count()
+    if not args.no_graph:
+        # graph replays do not pass the library's launch counter: the captured step holds exactly the
+        # kernels of one eager step, counted here
+        launches = launches_per_step * args.steps
     ops_ms = timer.summary()
     step_ms_instr = sum(v["ms"] for v in ops_ms.values())
-    top = max(ops_ms, key=lambda k: ops_ms[k]["ms"])
     peaks, peak_src = measured_peaks()
     fp64_peak = fp64_peak_tflops()
-    if top == "pde_gemm_f64":
-        t = ops_ms[top]
-        achieved = t["flop"] / (t["ms"] * 1e-3) / 1e12
-        roof = {"kernel": "k_gemm_f64 (DMMA; dense DCT-I + Poisson projections)", "bound": "tensor",
-                "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                "traffic": None, "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (fp64 tensor pipe; "
-                "MEASURED_PEAKS.json records no fp64 figure)",
-                "launches_per_step": t["launches"], "avg_launch_ms": t["ms"] / t["launches"],
-                "share_of_step": t["ms"] / step_ms_instr}
-    else:
-        t = ops_ms[top]
-        roof = {"kernel": top, "bound": "hbm", "achieved": None, "peak": peaks.get("hbm_gbs"), "unit": "GB/s",
-                "frac": None, "traffic": None, "peak_source": peak_src, "launches_per_step": t["launches"],
-                "avg_launch_ms": t["ms"] / t["launches"], "share_of_step": t["ms"] / step_ms_instr}
+    dct_ms = sum(v["ms"] for k, v in ops_ms.items() if k.startswith("pde_dct1"))
+    dct_work = sum(v["work"] for k, v in ops_ms.items() if k.startswith("pde_dct1"))
+    dct_launches = sum(v["launches"] for k, v in ops_ms.items() if k.startswith("pde_dct1"))
+    gemm = ops_ms.get("pde_gemm_f64", {"ms": 0.0, "work": 0.0, "launches": 1})
+    roof_dct = {"kernel": "k_dct_fft (shared-memory FFT DCT-I, all batched transforms of the step)", "bound": "hbm",
+                "achieved": dct_work / (dct_ms * 1e-3) / 1e9 if dct_ms else None, "peak": peaks.get("hbm_gbs"),
+                "unit": "GB/s", "traffic": None, "peak_source": peak_src, "launches_per_step": dct_launches,
+                "avg_launch_ms": dct_ms / max(dct_launches, 1), "share_of_step": dct_ms / step_ms_instr,
+                "algorithmic_bytes_per_launch": dct_work / max(dct_launches, 1)}
+    roof_dct["frac"] = roof_dct["achieved"] / roof_dct["peak"] if roof_dct["achieved"] else None
+    roof_gemm = {"kernel": "k_gemm_f64 (DMMA; Poisson projections Hy, Qy)", "bound": "tensor",
+                 "achieved": gemm["work"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] else None, "peak": fp64_peak,
+                 "unit": "TFLOP/s", "traffic": None,
+                 "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no fp64 entry)",
+                 "launches_per_step": gemm["launches"], "avg_launch_ms": gemm["ms"] / max(gemm["launches"], 1),
+                 "share_of_step": gemm["ms"] / step_ms_instr}
+    roof_gemm["frac"] = roof_gemm["achieved"] / fp64_peak if roof_gemm["achieved"] else None
+    roof = roof_dct if dct_ms >= gemm["ms"] else roof_gemm
+    roof_other = roof_gemm if roof is roof_dct else roof_dct
 
     # ---- CPU baseline: bounded sample of the same workload on rank 0 -----------------------
     cpu = None
@@ -375,12 +374,15 @@ def run_gpu(args, cfg):
                    "dealias": cfg["dealias"], "ra": cfg["ra"], "dt": cfg["dt"], "stages_per_step": nst,
                    "l2": "state + work arrays exceed the 126 MB L2 (no flush needed)" if N >= 1024
                    else "working set fits L2 (small-grid regime, by design of the workload)",
-                   "finite": finite, "setup_s": setup_s},
+                   "finite": finite, "setup_s": setup_s, "cuda_graph": not args.no_graph,
+                   "dealias_grid": list(ns.deriv_field.dealias.shape_physical) if cfg["dealias"] else None},
         "clocks": clocks,
         "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
         "gpu_launches": launches,
+        "gpu_launches_per_step": launches_per_step,
         "roofline": roof,
+        "roofline_second": roof_other,
         "step_model": {"algorithmic_bytes_per_step": stage_bytes * nst, "dense_flop_per_step": stage_flop * nst,
                        "hbm_fraction": (stage_bytes * nst / (peaks.get("hbm_gbs", 6650.0) * 1e9)) / (ms / args.steps * 1e-3),
                        "combined_fraction": (stage_bytes * nst / (peaks.get("hbm_gbs", 6650.0) * 1e9)
@@ -401,6 +403,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="rbc2048", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     cfg = WORKLOADS[args.workload]

@@ -132,6 +132,103 @@ int pde_poisson_solve(pde_poisson_plan_t plan, double *x, long ldx, void *stream
 int pde_gemm_f64(int transB, const double *A, long lda, const double *B, long ldb,
                  double *C, long ldc, int m, int n, int k, void *stream);
 
+
+/* ---- batched entry points -----------------------------------------------------------
+ * The time stepper applies the same operator to several arrays at once (the U, V, T
+ * fields; value and derivative of one field; ...).  These entry points take up to
+ * PDE_MAX_JOBS arrays per launch (blockIdx.y / .z = job), which multiplies the number of
+ * resident warps of the latency-bound sweeps and divides the number of launches.
+ * Job arrays are HOST arrays of plain structs (copied into kernel parameters). */
+#define PDE_MAX_JOBS 8
+
+/* One sequence sweep job (pde_sweep).  Element i of sequence q is in[s][i*ldin[s] + q]
+ * (axis 0) or in[s][q*ldin[s] + i] (axis 1); the result goes to out the same way
+ * (out may alias in[0]).  tab[] are per-index DEVICE tables, see the op list. */
+typedef struct {
+    const double *in[5];
+    long ldin[5];
+    double *out;
+    long ldout;
+    const double *tab[6];
+    const int *itab;
+    int nseq;
+    int flag;
+    double sc;
+} pde_sweep_job;
+
+/* ops of pde_sweep (reference recurrences: see pde_cheb_diff, pde_from_cheb, pde_fdma_solve,
+ * pde_twodma_solve, pde_poisson_solve; every solve is a forward and a backward sweep):
+ *   DIFF        in[0] = c                 flag/sc: divide the result by sc
+ *   TDMA_FWD    in[0] = u (in[1] = u too when tab[0] = stencil s is given: rhs = u_i + s_i u_{i+2});
+ *               tab: 1 = a, 2 = den, 4 = RN(1/den) (optional, same bits, shorter critical path)
+ *   TDMA_BWD    in[0] = g (usually == out), tab[3] = w
+ *   FDMA_FWD    tab[0] = l;   FDMA_BWD  tab: 1 = d, 2 = u1, 3 = u2, 4 = RN(1/d) (optional)
+ *   TWODMA_BWD  tab: 0 = d, 1 = u, 4 = RN(1/d) (optional)
+ *   POISSON_*   driven by pde_poisson_solve (per-column tables as extra streams) */
+#define PDE_SWEEP_DIFF 0
+#define PDE_SWEEP_TDMA_FWD 1
+#define PDE_SWEEP_TDMA_BWD 2
+#define PDE_SWEEP_FDMA_FWD 3
+#define PDE_SWEEP_FDMA_BWD 4
+#define PDE_SWEEP_TWODMA_BWD 5
+int pde_sweep(int op, int axis, int n, int njobs, const pde_sweep_job *jobs, void *stream);
+
+/* u = S v (pde_to_cheb) for several arrays */
+typedef struct {
+    const double *s;
+    const double *v;
+    long ldv;
+    int M;
+    double *u;
+    long ldu;
+    int n_out;
+    int batch;
+} pde_stencil_job;
+int pde_to_cheb_multi(int axis, int njobs, const pde_stencil_job *jobs, void *stream);
+
+/* y = A x or y += A x (pde_banded_mul) for several arrays */
+typedef struct {
+    const double *diags;
+    int ndiag;
+    int off[8];
+    const double *x;
+    long ldx;
+    int n_in;
+    double *y;
+    long ldy;
+    int n_out;
+    int batch;
+    int accumulate;
+} pde_band_job;
+int pde_banded_multi(int axis, int njobs, const pde_band_job *jobs, void *stream);
+
+/* y = (((c0 x0) + c1 x1) + c2 x2) + c3 x3, rounded after every product and sum like the
+ * NumPy expressions of navier/rbc2d.py:252-394 (a coefficient of exactly 1 is not multiplied);
+ * y may alias any x.  All arrays are (n0 x n1) row-major with their own leading dimension. */
+typedef struct {
+    int nterm;
+    const double *x[4];
+    long ldx[4];
+    double coef[4];
+    double *y;
+    long ldy;
+    int n0, n1;
+} pde_lincomb_job;
+int pde_lincomb_multi(int njobs, const pde_lincomb_job *jobs, void *stream);
+
+/* Pseudo-spectral products of one IMEX stage on the (dealiased) physical grid, n points
+ * (conv_term / convective_term, pypde/field_operations.py:83-169, with the two calls of an
+ * RK3 stage, navier/rbc2d.py:260-266, merged by linearity: ub = b u + c u_old):
+ *   dxU <- ub dxU + wb dzU,  dxV <- ub dxV + wb dzV,  dxT <- ub dxT + wb dzT + wb dTbc
+ * u_old / w_old may be NULL when c == 0; dTbc may be NULL. */
+int pde_conv_products(long n, double b, double c, const double *u, const double *w, const double *u_old,
+                      const double *w_old, double *dxU, const double *dzU, double *dxV, const double *dzV,
+                      double *dxT, const double *dzT, const double *dTbc, void *stream);
+
+/* pde_dct1 on several arrays of identical shape */
+int pde_dct1_multi(pde_dct_plan_t plan, int mode, int njobs, const double *const *x, long ldx, int n_in,
+                   double *const *y, long ldy, int n_out, int batch, int axis, void *stream);
+
 /* ---- layout helper ------------------------------------------------------------- */
 /* out(n1 x n0) = in(n0 x n1)^T */
 int pde_transpose(const double *in, long ldin, double *out, long ldout, int n0, int n1, void *stream);

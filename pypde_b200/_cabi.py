@@ -55,6 +55,44 @@ SIGNATURES = {
     "pde_transpose": (_c_int, [_c_dp, _c_long, _c_dp, _c_long, _c_int, _c_int, ctypes.c_void_p]),
 }
 
+class SweepJob(ctypes.Structure):
+    """pde_sweep_job (include/pypde_b200.h)"""
+    _fields_ = [("inp", ctypes.c_void_p * 5), ("ldin", ctypes.c_long * 5), ("out", ctypes.c_void_p),
+                ("ldout", ctypes.c_long), ("tab", ctypes.c_void_p * 6), ("itab", ctypes.c_void_p),
+                ("nseq", ctypes.c_int), ("flag", ctypes.c_int), ("sc", ctypes.c_double)]
+
+
+class StencilJob(ctypes.Structure):
+    """pde_stencil_job"""
+    _fields_ = [("s", ctypes.c_void_p), ("v", ctypes.c_void_p), ("ldv", ctypes.c_long), ("M", ctypes.c_int),
+                ("u", ctypes.c_void_p), ("ldu", ctypes.c_long), ("n_out", ctypes.c_int), ("batch", ctypes.c_int)]
+
+
+class BandJob(ctypes.Structure):
+    """pde_band_job"""
+    _fields_ = [("diags", ctypes.c_void_p), ("ndiag", ctypes.c_int), ("off", ctypes.c_int * 8),
+                ("x", ctypes.c_void_p), ("ldx", ctypes.c_long), ("n_in", ctypes.c_int), ("y", ctypes.c_void_p),
+                ("ldy", ctypes.c_long), ("n_out", ctypes.c_int), ("batch", ctypes.c_int),
+                ("accumulate", ctypes.c_int)]
+
+
+class LincombJob(ctypes.Structure):
+    """pde_lincomb_job"""
+    _fields_ = [("nterm", ctypes.c_int), ("x", ctypes.c_void_p * 4), ("ldx", ctypes.c_long * 4),
+                ("coef", ctypes.c_double * 4), ("y", ctypes.c_void_p), ("ldy", ctypes.c_long),
+                ("n0", ctypes.c_int), ("n1", ctypes.c_int)]
+
+
+SIGNATURES.update({
+    "pde_sweep": (_c_int, [_c_int, _c_int, _c_int, _c_int, ctypes.POINTER(SweepJob), ctypes.c_void_p]),
+    "pde_to_cheb_multi": (_c_int, [_c_int, _c_int, ctypes.POINTER(StencilJob), ctypes.c_void_p]),
+    "pde_banded_multi": (_c_int, [_c_int, _c_int, ctypes.POINTER(BandJob), ctypes.c_void_p]),
+    "pde_lincomb_multi": (_c_int, [_c_int, ctypes.POINTER(LincombJob), ctypes.c_void_p]),
+    "pde_conv_products": (_c_int, [_c_long, ctypes.c_double, ctypes.c_double] + [_c_dp] * 11 + [ctypes.c_void_p]),
+    "pde_dct1_multi": (_c_int, [ctypes.c_void_p, _c_int, _c_int, ctypes.POINTER(ctypes.c_void_p), _c_long, _c_int,
+                                ctypes.POINTER(ctypes.c_void_p), _c_long, _c_int, _c_int, _c_int, ctypes.c_void_p]),
+})
+
 _lib = None
 
 

@@ -20,7 +20,7 @@ LIB = os.path.join(OUT, "libpypde_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 # banded.cu keeps the Fortran operation order (bit parity with the oracle): no FMA contraction
-PER_FILE = {"banded.cu": ["--fmad=false"]}
+PER_FILE = {"banded.cu": ["--fmad=false"], "batched.cu": ["--fmad=false"]}
 
 
 def _nvcc():

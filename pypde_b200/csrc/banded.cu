@@ -68,6 +68,7 @@ __global__ void k_banded_mul(DiagSpec spec, const double *__restrict__ diags, co
 // ---------------------------------------------------------------------------
 struct PoissonTables {
     double *l, *d, *u1, *u2;   // (n x m) row-major each
+    double *rd;                // RN(1/d), for the correctly rounded fast division
     int *off;                  // 1 where the singular branch drops row/col 0
 };
 
@@ -99,6 +100,8 @@ __global__ void k_poisson_factor(const double *__restrict__ Ad, const double *__
         T(t.d, q) = T(t.d, q) - lf * T(t.u1, q - 2);
         if (q < ne - 2) T(t.u1, q) = T(t.u1, q) - lf * T(t.u2, q - 2);
     }
+    for (int q = 0; q < ne; ++q) T(t.rd, q) = 1.0 / T(t.d, q);
+    if (off) t.rd[j] = 1.0;
 #undef T
 }
 
@@ -295,6 +298,7 @@ int pde_poisson_plan_create(pde_poisson_plan_t *plan, const double *Adiag, const
     PDE_CUDA(cudaMalloc(&p->t.d, tb));
     PDE_CUDA(cudaMalloc(&p->t.u1, tb));
     PDE_CUDA(cudaMalloc(&p->t.u2, tb));
+    PDE_CUDA(cudaMalloc(&p->t.rd, tb));
     PDE_CUDA(cudaMalloc(&p->t.off, sizeof(int) * m));
     PDE_CUDA(cudaMalloc(&dA, sizeof(double) * 4 * n));
     PDE_CUDA(cudaMalloc(&dC, sizeof(double) * 4 * n));
@@ -320,6 +324,7 @@ int pde_poisson_plan_destroy(pde_poisson_plan_t p)
     cudaFree(p->t.d);
     cudaFree(p->t.u1);
     cudaFree(p->t.u2);
+    cudaFree(p->t.rd);
     cudaFree(p->t.off);
     delete p;
     return PDE_OK;
@@ -340,7 +345,8 @@ int pde_poisson_solve(pde_poisson_plan_t p, double *x, long ldx, void *stream)
     jobs.j[0].in[1] = p->t.d;
     jobs.j[0].in[2] = p->t.u1;
     jobs.j[0].in[3] = p->t.u2;
-    jobs.j[0].ldin[1] = jobs.j[0].ldin[2] = jobs.j[0].ldin[3] = p->m;
+    jobs.j[0].in[4] = p->t.rd;
+    jobs.j[0].ldin[1] = jobs.j[0].ldin[2] = jobs.j[0].ldin[3] = jobs.j[0].ldin[4] = p->m;
     return launch_sweep<PoissonBwd>(jobs, 0, as_stream(stream), "pde_poisson_solve(bwd)");
 }
 

@@ -1,0 +1,200 @@
+// Batched (multi-array) entry points of the C ABI: pointwise stencil / banded / linear-
+// combination kernels, the pseudo-spectral products, and the generic sweep dispatcher.
+// Compiled with --fmad=false: every product and sum is rounded separately, like the
+// NumPy / SciPy expressions of the reference.
+#include "common.cuh"
+#include "sweeps.cuh"
+
+namespace pde {
+
+struct StencilJobs {
+    int njobs;
+    pde_stencil_job j[PDE_MAX_JOBS];
+};
+
+__global__ void k_to_cheb_multi(StencilJobs jobs, int axis)
+{
+    const pde_stencil_job &jb = jobs.j[blockIdx.z];
+    const int n0 = axis == 0 ? jb.n_out : jb.batch, n1 = axis == 0 ? jb.batch : jb.n_out;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= n0 || j >= n1) return;
+    const int k = axis == 0 ? i : j;
+    const long step = axis == 0 ? jb.ldv : 1;
+    const double *vp = jb.v + (long)i * jb.ldv + j;
+    double acc = 0.0;
+    if (k >= 2 && k - 2 < jb.M) {
+        const double sk = __ldg(jb.s + k - 2);
+        if (sk != 0.0) acc = sk * vp[-2 * step];
+    }
+    if (k < jb.M) acc = acc + vp[0];
+    jb.u[(long)i * jb.ldu + j] = acc;
+}
+
+struct BandJobs {
+    int njobs;
+    pde_band_job j[PDE_MAX_JOBS];
+};
+
+__global__ void k_banded_multi(BandJobs jobs, int axis)
+{
+    const pde_band_job &jb = jobs.j[blockIdx.z];
+    const int n0 = axis == 0 ? jb.n_out : jb.batch, n1 = axis == 0 ? jb.batch : jb.n_out;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= n0 || j >= n1) return;
+    const int r = axis == 0 ? i : j;
+    double acc = 0.0;
+    for (int d = 0; d < jb.ndiag; ++d) {
+        const int c = r + jb.off[d];
+        if (c < 0 || c >= jb.n_in) continue;
+        const double a = __ldg(jb.diags + (long)d * jb.n_out + r);
+        if (a == 0.0) continue;
+        const double xv = axis == 0 ? jb.x[(long)c * jb.ldx + j] : jb.x[(long)i * jb.ldx + c];
+        acc = acc + a * xv;
+    }
+    double *yp = jb.y + (long)i * jb.ldy + j;
+    *yp = jb.accumulate ? *yp + acc : acc;
+}
+
+struct LincombJobs {
+    int njobs;
+    pde_lincomb_job j[PDE_MAX_JOBS];
+};
+
+__global__ void k_lincomb_multi(LincombJobs jobs)
+{
+    const pde_lincomb_job &jb = jobs.j[blockIdx.z];
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= jb.n0 || j >= jb.n1) return;
+    double acc = 0.0;
+    for (int t = 0; t < jb.nterm; ++t) {
+        const double xv = jb.x[t][(long)i * jb.ldx[t] + j];
+        const double term = jb.coef[t] == 1.0 ? xv : jb.coef[t] * xv;
+        acc = t == 0 ? term : acc + term;
+    }
+    jb.y[(long)i * jb.ldy + j] = acc;
+}
+
+__global__ void k_conv_products(long n, double b, double c, const double *__restrict__ u,
+                                const double *__restrict__ w, const double *__restrict__ uo,
+                                const double *__restrict__ wo, double *dxU, const double *__restrict__ dzU,
+                                double *dxV, const double *__restrict__ dzV, double *dxT,
+                                const double *__restrict__ dzT, const double *__restrict__ dTbc)
+{
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        double ub = u[i], wb = w[i];
+        if (uo != nullptr) {
+            ub = b * ub + c * uo[i];
+            wb = b * wb + c * wo[i];
+        } else if (b != 1.0) {
+            ub = b * ub;
+            wb = b * wb;
+        }
+        dxU[i] = dxU[i] * ub + dzU[i] * wb;
+        dxV[i] = dxV[i] * ub + dzV[i] * wb;
+        double t = dxT[i] * ub + dzT[i] * wb;
+        if (dTbc != nullptr) t = t + wb * dTbc[i];
+        dxT[i] = t;
+    }
+}
+
+}  // namespace pde
+
+using namespace pde;
+
+extern "C" {
+
+int pde_sweep(int op, int axis, int n, int njobs, const pde_sweep_job *jobs, void *stream)
+{
+    PDE_REQUIRE(jobs && njobs >= 1 && njobs <= PDE_MAX_JOBS, "1..8 jobs");
+    PDE_REQUIRE(axis == 0 || axis == 1, "axis");
+    PDE_REQUIRE(n >= 5, "n >= 5");
+    SweepJobs sj{};
+    sj.njobs = njobs;
+    sj.n = n;
+    for (int j = 0; j < njobs; ++j) sj.j[j] = jobs[j];
+    cudaStream_t st = as_stream(stream);
+    switch (op) {
+    case PDE_SWEEP_DIFF: return launch_sweep<DiffDesc>(sj, axis, st, "pde_sweep(diff)");
+    case PDE_SWEEP_TDMA_FWD: return launch_sweep<TdmaFwd>(sj, axis, st, "pde_sweep(tdma fwd)");
+    case PDE_SWEEP_TDMA_BWD: return launch_sweep<TdmaBwd>(sj, axis, st, "pde_sweep(tdma bwd)");
+    case PDE_SWEEP_FDMA_FWD: return launch_sweep<FdmaFwd>(sj, axis, st, "pde_sweep(fdma fwd)");
+    case PDE_SWEEP_FDMA_BWD: return launch_sweep<FdmaBwd>(sj, axis, st, "pde_sweep(fdma bwd)");
+    case PDE_SWEEP_TWODMA_BWD: return launch_sweep<TwodmaBwd>(sj, axis, st, "pde_sweep(twodma)");
+    default: set_error("pde_sweep: unknown op %d", op); return PDE_ERR_ARG;
+    }
+}
+
+int pde_to_cheb_multi(int axis, int njobs, const pde_stencil_job *jobs, void *stream)
+{
+    PDE_REQUIRE(jobs && njobs >= 1 && njobs <= PDE_MAX_JOBS, "1..8 jobs");
+    PDE_REQUIRE(axis == 0 || axis == 1, "axis");
+    StencilJobs sj{};
+    sj.njobs = njobs;
+    int m0 = 0, m1 = 0;
+    for (int j = 0; j < njobs; ++j) {
+        sj.j[j] = jobs[j];
+        const int n0 = axis == 0 ? jobs[j].n_out : jobs[j].batch, n1 = axis == 0 ? jobs[j].batch : jobs[j].n_out;
+        m0 = n0 > m0 ? n0 : m0;
+        m1 = n1 > m1 ? n1 : m1;
+    }
+    if (m0 <= 0 || m1 <= 0) return PDE_OK;
+    dim3 block(64, 4), grid(ceil_div(m1, 64), ceil_div(m0, 4), njobs);
+    k_to_cheb_multi<<<grid, block, 0, as_stream(stream)>>>(sj, axis);
+    return after_launch("pde_to_cheb_multi");
+}
+
+int pde_banded_multi(int axis, int njobs, const pde_band_job *jobs, void *stream)
+{
+    PDE_REQUIRE(jobs && njobs >= 1 && njobs <= PDE_MAX_JOBS, "1..8 jobs");
+    PDE_REQUIRE(axis == 0 || axis == 1, "axis");
+    BandJobs bj{};
+    bj.njobs = njobs;
+    int m0 = 0, m1 = 0;
+    for (int j = 0; j < njobs; ++j) {
+        PDE_REQUIRE(jobs[j].ndiag >= 1 && jobs[j].ndiag <= 8, "1..8 diagonals");
+        bj.j[j] = jobs[j];
+        const int n0 = axis == 0 ? jobs[j].n_out : jobs[j].batch, n1 = axis == 0 ? jobs[j].batch : jobs[j].n_out;
+        m0 = n0 > m0 ? n0 : m0;
+        m1 = n1 > m1 ? n1 : m1;
+    }
+    if (m0 <= 0 || m1 <= 0) return PDE_OK;
+    dim3 block(64, 4), grid(ceil_div(m1, 64), ceil_div(m0, 4), njobs);
+    k_banded_multi<<<grid, block, 0, as_stream(stream)>>>(bj, axis);
+    return after_launch("pde_banded_multi");
+}
+
+int pde_lincomb_multi(int njobs, const pde_lincomb_job *jobs, void *stream)
+{
+    PDE_REQUIRE(jobs && njobs >= 1 && njobs <= PDE_MAX_JOBS, "1..8 jobs");
+    LincombJobs lj{};
+    lj.njobs = njobs;
+    int m0 = 0, m1 = 0;
+    for (int j = 0; j < njobs; ++j) {
+        PDE_REQUIRE(jobs[j].nterm >= 1 && jobs[j].nterm <= 4, "1..4 terms");
+        lj.j[j] = jobs[j];
+        m0 = jobs[j].n0 > m0 ? jobs[j].n0 : m0;
+        m1 = jobs[j].n1 > m1 ? jobs[j].n1 : m1;
+    }
+    if (m0 <= 0 || m1 <= 0) return PDE_OK;
+    dim3 block(64, 4), grid(ceil_div(m1, 64), ceil_div(m0, 4), njobs);
+    k_lincomb_multi<<<grid, block, 0, as_stream(stream)>>>(lj);
+    return after_launch("pde_lincomb_multi");
+}
+
+int pde_conv_products(long n, double b, double c, const double *u, const double *w, const double *u_old,
+                      const double *w_old, double *dxU, const double *dzU, double *dxV, const double *dzV,
+                      double *dxT, const double *dzT, const double *dTbc, void *stream)
+{
+    PDE_REQUIRE(u && w && dxU && dzU && dxV && dzV && dxT && dzT, "null pointer");
+    PDE_REQUIRE((u_old == nullptr) == (w_old == nullptr), "u_old and w_old go together");
+    if (n <= 0) return PDE_OK;
+    const int grid = (int)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+    k_conv_products<<<grid, 256, 0, as_stream(stream)>>>(n, b, c, u, w, u_old, w_old, dxU, dzU, dxV, dzV, dxT,
+                                                         dzT, dTbc);
+    return after_launch("pde_conv_products");
+}
+
+}  // extern "C"

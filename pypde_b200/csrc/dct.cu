@@ -24,8 +24,8 @@ struct FftDctPlan;
 int fft_dct_supported(int L);
 int fft_dct_create(FftDctPlan **p, int L);
 void fft_dct_destroy(FftDctPlan *p);
-int fft_dct_exec(FftDctPlan *p, int mode, const double *x, long ldx, int n_in, double *y, long ldy,
-                 int n_out, int batch, int axis, cudaStream_t st);
+int fft_dct_exec(FftDctPlan *p, int mode, int njobs, const double *const *xs, long ldx, int n_in,
+                 double *const *ys, long ldy, int n_out, int batch, int axis, cudaStream_t st);
 
 // cos(pi * r / P) for integers 0 <= r, P > 0, accurate to long-double rounding
 static long double cos_pi_frac(long long r, long long P)
@@ -128,24 +128,33 @@ int pde_dct_plan_destroy(pde_dct_plan_t p)
 
 int pde_dct_plan_algo(pde_dct_plan_t p) { return p ? p->algo : 0; }
 
-int pde_dct1(pde_dct_plan_t p, int mode, const double *x, long ldx, int n_in, double *y, long ldy,
-             int n_out, int batch, int axis, void *stream)
+int pde_dct1_multi(pde_dct_plan_t p, int mode, int njobs, const double *const *x, long ldx, int n_in,
+                   double *const *y, long ldy, int n_out, int batch, int axis, void *stream)
 {
     PDE_REQUIRE(p && x && y, "null pointer");
+    PDE_REQUIRE(njobs >= 1 && njobs <= PDE_MAX_JOBS, "1..8 jobs");
     PDE_REQUIRE(mode >= 0 && mode <= 2, "mode");
     PDE_REQUIRE(axis == 0 || axis == 1, "axis");
     PDE_REQUIRE(n_in >= 1 && n_in <= p->L && n_out >= 1 && n_out <= p->L, "n_in / n_out in 1..L");
-    PDE_REQUIRE(x != y, "in-place transform not supported");
+    for (int j = 0; j < njobs; ++j) PDE_REQUIRE(x[j] && y[j] && x[j] != y[j], "null / in-place transform");
     if (batch <= 0) return PDE_OK;
     cudaStream_t st = as_stream(stream);
     if (p->algo != 1)
-        return fft_dct_exec(p->fft, mode, x, ldx, n_in, y, ldy, n_out, batch, axis, st);
+        return fft_dct_exec(p->fft, mode, njobs, x, ldx, n_in, y, ldy, n_out, batch, axis, st);
     int rc = build_dense(p, mode);
-    if (rc != PDE_OK) return rc;
-    if (axis == 0)   // Y(n_out x batch) = Mat(n_out x n_in) X(n_in x batch)
-        return gemm_f64(false, p->mat[mode], p->ldm, x, ldx, y, ldy, n_out, batch, n_in, st);
-    // Y(batch x n_out) = X(batch x n_in) Mat(n_out x n_in)^T
-    return gemm_f64(true, x, ldx, p->mat[mode], p->ldm, y, ldy, batch, n_out, n_in, st);
+    for (int j = 0; j < njobs && rc == PDE_OK; ++j) {
+        if (axis == 0)   // Y(n_out x batch) = Mat(n_out x n_in) X(n_in x batch)
+            rc = gemm_f64(false, p->mat[mode], p->ldm, x[j], ldx, y[j], ldy, n_out, batch, n_in, st);
+        else             // Y(batch x n_out) = X(batch x n_in) Mat(n_out x n_in)^T
+            rc = gemm_f64(true, x[j], ldx, p->mat[mode], p->ldm, y[j], ldy, batch, n_out, n_in, st);
+    }
+    return rc;
+}
+
+int pde_dct1(pde_dct_plan_t p, int mode, const double *x, long ldx, int n_in, double *y, long ldy,
+             int n_out, int batch, int axis, void *stream)
+{
+    return pde_dct1_multi(p, mode, 1, &x, ldx, n_in, &y, ldy, n_out, batch, axis, stream);
 }
 
 }  // extern "C"

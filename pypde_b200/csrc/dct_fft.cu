@@ -38,6 +38,11 @@ struct PassList {
     int radix[24];
 };
 
+struct DctPtrs {                 // blockIdx.y selects the array (pde_dct1_multi)
+    const double *x[PDE_MAX_JOBS];
+    double *y[PDE_MAX_JOBS];
+};
+
 // ---- small DFTs (forward, exp(-2 pi i qr/R)) -------------------------------------------
 __device__ __forceinline__ double2 cadd(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 csub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
@@ -155,10 +160,12 @@ __device__ __forceinline__ double in_scale(int mode, int n, int P, double v)
 template <int AXIS>
 __global__ void __launch_bounds__(1024)
 k_dct_fft(PassList pl, const double2 *__restrict__ W, const double2 *__restrict__ CS,
-          const int *__restrict__ pos, int P, int mode, const double *__restrict__ x, long ldx, int n_in,
-          double *__restrict__ y, long ldy, int n_out, int batch, int S)
+          const int *__restrict__ pos, int P, int mode, DctPtrs ptrs, long ldx, int n_in,
+          long ldy, int n_out, int batch, int S)
 {
     extern __shared__ __align__(16) double2 zsm[];
+    const double *__restrict__ x = ptrs.x[blockIdx.y];
+    double *__restrict__ y = ptrs.y[blockIdx.y];
     const int q0 = blockIdx.x * S;
     const int ns = min(S, batch - q0);
     // ---- load: z_m = e_{2m} + i e_{2m+1}, e = even extension of the (scaled, zero padded) input
@@ -310,9 +317,14 @@ void fft_dct_destroy(FftDctPlan *p)
     delete p;
 }
 
-int fft_dct_exec(FftDctPlan *p, int mode, const double *x, long ldx, int n_in, double *y, long ldy, int n_out,
-                 int batch, int axis, cudaStream_t st)
+int fft_dct_exec(FftDctPlan *p, int mode, int njobs, const double *const *xs, long ldx, int n_in,
+                 double *const *ys, long ldy, int n_out, int batch, int axis, cudaStream_t st)
 {
+    DctPtrs ptrs{};
+    for (int j = 0; j < njobs; ++j) {
+        ptrs.x[j] = xs[j];
+        ptrs.y[j] = ys[j];
+    }
     const int P = p->P;
     const size_t per_seq = (size_t)P * 16;
     // sequences per CTA: aim at <= ~100 KB (2 CTAs/SM); axis 0 wants >= 4 columns for full sectors
@@ -321,20 +333,20 @@ int fft_dct_exec(FftDctPlan *p, int mode, const double *x, long ldx, int n_in, d
     if (axis == 0 && S < 4) S = (int)((200 * 1024) / per_seq) >= 4 ? 4 : (int)((200 * 1024) / per_seq);
     if (S > 16) S = 16;
     // keep the grid at >= ~2 waves when the batch allows it
-    while (S > (axis == 0 ? 4 : 1) && ceil_div(batch, S) < 2 * sm_count()) S >>= 1;
+    while (S > (axis == 0 ? 4 : 1) && ceil_div(batch, S) * njobs < 2 * sm_count()) S >>= 1;
     if (S < 1) S = 1;
     PassList pl;
     pl.npass = p->npass;
     for (int i = 0; i < p->npass; ++i) pl.radix[i] = p->radix[i];
     const size_t smem = per_seq * S;
-    const int grid = ceil_div(batch, S);
+    const dim3 grid(ceil_div(batch, S), njobs);
     // >= 2 radix-4 butterflies per thread and pass; more warps hide the twiddle / smem latency
     int T = 128;
     while (T < 1024 && (long)T * 8 < (long)S * P) T <<= 1;
     if (axis == 1)
-        k_dct_fft<1><<<grid, T, smem, st>>>(pl, p->W, p->CS, p->pos, P, mode, x, ldx, n_in, y, ldy, n_out, batch, S);
+        k_dct_fft<1><<<grid, T, smem, st>>>(pl, p->W, p->CS, p->pos, P, mode, ptrs, ldx, n_in, ldy, n_out, batch, S);
     else
-        k_dct_fft<0><<<grid, T, smem, st>>>(pl, p->W, p->CS, p->pos, P, mode, x, ldx, n_in, y, ldy, n_out, batch, S);
+        k_dct_fft<0><<<grid, T, smem, st>>>(pl, p->W, p->CS, p->pos, P, mode, ptrs, ldx, n_in, ldy, n_out, batch, S);
     return after_launch("pde_dct1(fft)");
 }
 

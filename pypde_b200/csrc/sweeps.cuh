@@ -28,19 +28,9 @@ static_assert(true, "");
 constexpr int SW_KC = 4;         // chunks in the ring (SW_KC-1 chunks = 24 steps in flight per thread)
 constexpr int RING_K = SW_C * SW_KC;
 constexpr int SWEEP_MAX_JOBS = 8;
-constexpr int SWEEP_MAX_IN = 4;
+constexpr int SWEEP_MAX_IN = 5;
 
-struct SweepJob {
-    const double *in[SWEEP_MAX_IN];
-    long ldin[SWEEP_MAX_IN];
-    double *out;
-    long ldout;
-    const double *tab[5];      // per-index coefficient tables (shared by all sequences)
-    const int *itab;           // per-sequence integer table (Poisson: singular offset)
-    int nseq;
-    int flag;
-    double sc;
-};
+using SweepJob = pde_sweep_job;   // layout shared with the C ABI (include/pypde_b200.h)
 
 struct SweepJobs {
     int njobs;
@@ -56,6 +46,30 @@ __device__ __forceinline__ void cp_async_8(double *smem, const double *gmem)
 __device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// Correctly rounded a / d from the precomputed correctly rounded reciprocal rd = RN(1/d):
+// q = a rd is within ~1 ulp, one FMA residual + correction makes it faithful to ~2^-105, the
+// second one rounds it to RN(a/d) (Markstein's theorem).  5 dependent FP64 ops instead of the
+// ~25-instruction generic division on the recurrence's critical path; same bits.
+__device__ __forceinline__ double div_rn(double a, double d, const double *rdp, int i)
+{
+    if (rdp == nullptr) return a / d;
+    const double rd = __ldg(rdp + i);
+    double q = a * rd;
+    double r = __fma_rn(-q, d, a);
+    q = __fma_rn(r, rd, q);
+    r = __fma_rn(-q, d, a);
+    return __fma_rn(r, rd, q);
+}
+__device__ __forceinline__ double div_rn_v(double a, double d, double rd, bool have)
+{
+    if (!have) return a / d;
+    double q = a * rd;
+    double r = __fma_rn(-q, d, a);
+    q = __fma_rn(r, rd, q);
+    r = __fma_rn(-q, d, a);
+    return __fma_rn(r, rd, q);
+}
 
 template <bool LC>
 struct Writer {
@@ -241,7 +255,7 @@ struct DiffDesc {
 
 // tdma.f90:55-106, k = 2, forward part: g_i = (rhs_i - a_{i-2} g_{i-2}) / den_i with the fused
 // S^T product rhs_i = u_i + s_i u_{i+2} (chebyshev.py:327) when tab[0] = s is given.
-// tab: 0 = s (or null), 1 = a, 2 = den.
+// tab: 0 = s (or null), 1 = a, 2 = den, 3 = w (back substitution), 4 = RN(1/den) (optional).
 struct TdmaFwd {
     static constexpr int NIN = 2;
     static constexpr bool ASC = true;
@@ -262,7 +276,7 @@ struct TdmaFwd {
         if (job.tab[0]) rhs = v[0] + __ldg(job.tab[0] + i) * v[1];
         double g;
         if (!MID && i < 2) g = rhs / __ldg(job.tab[2] + i);
-        else g = (rhs - __ldg(job.tab[1] + i - 2) * ((i & 1) ? s.g1 : s.g0)) / __ldg(job.tab[2] + i);
+        else g = div_rn(rhs - __ldg(job.tab[1] + i - 2) * ((i & 1) ? s.g1 : s.g0), __ldg(job.tab[2] + i), job.tab[4], i);
         if (i & 1) s.g1 = g;
         else s.g0 = g;
         out.st(i, g);
@@ -292,7 +306,7 @@ struct TdmaBwd {
     }
 };
 
-// fdma.f90:26-36: forward x_i -= l_{i-2} x_{i-2}; tab: 0 = l, 1 = d, 2 = u1, 3 = u2
+// fdma.f90:26-36: forward x_i -= l_{i-2} x_{i-2}; tab: 0 = l, 1 = d, 2 = u1, 3 = u2, 4 = RN(1/d) (optional)
 struct FdmaFwd {
     static constexpr int NIN = 1;
     static constexpr bool ASC = true;
@@ -332,7 +346,7 @@ struct FdmaBwd {
         double x;
         if (!MID && i >= n - 2) x = v[0] / d;
         else if (!MID && i >= n - 4) x = (v[0] - __ldg(job.tab[2] + i) * x2) / d;
-        else x = (v[0] - __ldg(job.tab[2] + i) * x2 - __ldg(job.tab[3] + i) * x4) / d;
+        else x = div_rn(v[0] - __ldg(job.tab[2] + i) * x2 - __ldg(job.tab[3] + i) * x4, d, job.tab[4], i);
         out.st(i, x);
         if (i & 1) {
             s.b4 = s.b2;
@@ -360,7 +374,7 @@ struct TwodmaBwd {
         const double d = __ldg(job.tab[0] + i);
         double x;
         if (!MID && i >= n - 2) x = v[0] / d;
-        else x = (v[0] - __ldg(job.tab[1] + i) * ((i & 1) ? s.x1 : s.x0)) / d;
+        else x = div_rn(v[0] - __ldg(job.tab[1] + i) * ((i & 1) ? s.x1 : s.x0), d, job.tab[4], i);
         out.st(i, x);
         if (i & 1) s.x1 = x;
         else s.x0 = x;
@@ -401,9 +415,9 @@ struct PoissonFwd {
     }
 };
 
-// streams: 0 = x, 1 = D, 2 = U1, 3 = U2
+// streams: 0 = x, 1 = D, 2 = U1, 3 = U2, 4 = RN(1/D) (optional)
 struct PoissonBwd {
-    static constexpr int NIN = 4;
+    static constexpr int NIN = 5;
     static constexpr bool ASC = false;
     __device__ static int off(int) { return 0; }
     __device__ static int len(int, int n, const SweepJob &) { return n; }
@@ -417,14 +431,14 @@ struct PoissonBwd {
         s.off = job.itab[q];
     }
     template <bool MID, class W>
-    __device__ static void step(State &s, const SweepJob &, int n, int i, const double *v, W &out)
+    __device__ static void step(State &s, const SweepJob &job, int n, int i, const double *v, W &out)
     {
         if (!MID && i < s.off) return;
         const double x2 = (i & 1) ? s.b2 : s.a2, x4 = (i & 1) ? s.b4 : s.a4;
         double x;
         if (!MID && i >= n - 2) x = v[0] / v[1];
         else if (!MID && i >= n - 4) x = (v[0] - v[2] * x2) / v[1];
-        else x = (v[0] - v[2] * x2 - v[3] * x4) / v[1];
+        else x = div_rn_v(v[0] - v[2] * x2 - v[3] * x4, v[1], v[4], job.in[4] != nullptr);
         out.st(i, x);
         if (i & 1) {
             s.b4 = s.b2;

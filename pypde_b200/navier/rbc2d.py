@@ -35,14 +35,22 @@ class NavierStokes(NavierStokesBase, Integrator):
 
     avail_cases = ["rbc", "linear", "zero"]
 
-    def __init__(self, case="rbc", dealias_grid="fft", **kwargs):
+    def __init__(self, case="rbc", dealias_grid="fft", stepper="fast", graph=False, **kwargs):
         """dealias_grid: "fft" (default) evaluates the 3/2-rule products on the next
         FFT-friendly Gauss-Lobatto grid >= 3N/2 (same truncated coefficients up to rounding);
-        "reference" uses exactly int(3N/2) points like the reference."""
+        "reference" uses exactly int(3N/2) points like the reference.
+        stepper: "fast" (default) runs the batched stage of fast_stepper.FastStepper,
+        "reference" the operator-by-operator sequence of the reference (update_reference).
+        graph: capture the whole time step in a CUDA graph (removes launch overhead on
+        small grids)."""
         if case not in self.avail_cases:
             raise ValueError("Specified case is not available: ", self.avail_cases)
         self.case = case
         self.dealias_grid = dealias_grid
+        self._stepper_kind = stepper
+        self._use_graph = graph
+        self._fast = None
+        self._graph = None
         with dealias_policy(dealias_grid):
             self._construct(**kwargs)
 
@@ -115,7 +123,7 @@ class NavierStokes(NavierStokesBase, Integrator):
         self._finish_fieldbc()
 
     # -- solver plans (rbc2d.py:180-211) --------------------------------------------------
-    def setup_solver(self):
+    def _setup_solver_plans(self):
         from ..templates.hholtz import solverplan_hholtz2d_adi
         from ..templates.poisson import solverplan_poisson2d
 
@@ -196,9 +204,44 @@ class NavierStokes(NavierStokesBase, Integrator):
         self.pres.vhat -= float(1.0 * self.nu) * div * float(self.beta)
         self.pres.vhat += float(1.0 / (self.dt * self.a[stage])) * galerkin_to_cheby(self.P.vhat, self.P)
 
+    def setup_solver(self):
+        self._setup_solver_plans()
+        self._fast = None          # tables changed: rebuild the batched stepper lazily
+        self._graph = None
+
     def update(self):
-        """One time step = nstage IMEX stages, in the reference's operation order
-        (rbc2d.py:396-434)."""
+        """One time step = nstage IMEX stages (rbc2d.py:396-434)."""
+        if self._stepper_kind != "fast" or self.beta != 1.0:
+            return self.update_reference()
+        if self._fast is None:
+            from .fast_stepper import FastStepper
+            self._fast = FastStepper(self)
+        if not self._use_graph:
+            for rk in range(self.nstage):
+                self._fast.stage(rk)
+        else:
+            self._update_graph()
+        self.ux, self.uz = self._fast.ux, self._fast.uz
+
+    def _update_graph(self):
+        fs = self._fast
+        cur = tuple(t.data_ptr() for t in (self.T.vhat, self.U.vhat, self.V.vhat, self.P.vhat, self.pres.vhat))
+        if self._graph is None or cur != fs.bound:
+            fs.bind()
+            for rk in range(self.nstage):      # warm-up outside the capture (plan tables, attributes)
+                fs.stage_calls[rk].run()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for rk in range(self.nstage):
+                    fs.stage_calls[rk].run()
+            self._graph = g
+            # the warm-up advanced the state by one step already
+            return
+        self._graph.replay()
+
+    def update_reference(self):
+        """One time step, operator by operator in the reference's order (rbc2d.py:396-434)."""
         self.ux_old, self.uz_old = 0, 0
         for rk in range(self.nstage):
             That = galerkin_to_cheby(self.T.vhat, self.T)
