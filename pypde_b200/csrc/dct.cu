@@ -94,8 +94,9 @@ int pde_dct_plan_create(pde_dct_plan_t *plan, int L, int algo)
     PDE_REQUIRE(L >= 2, "DCT-I needs L >= 2");
     PDE_REQUIRE(algo >= 0 && algo <= 3, "algo in 0..3");
     if (algo == 0) {
-        if (L <= 256) algo = 1;
-        else algo = fft_dct_supported(L) ? fft_dct_supported(L) : 1;
+        // FFT whenever L-1 is even and smooth (specialised kernels exist from P = 96 on); the dense
+        // DMMA matrix for very short or awkward lengths
+        algo = (L >= 49 && fft_dct_supported(L)) ? fft_dct_supported(L) : 1;
     }
     pde_dct_plan_s *p = new pde_dct_plan_s();
     p->L = L;

@@ -230,6 +230,10 @@ k_dct_fft(PassList pl, const double2 *__restrict__ W, const double2 *__restrict_
     }
 }
 
+}  // namespace pde
+#include "dct_fft_t.cuh"
+namespace pde {
+
 // ---------------------------------------------------------------------------------------
 static bool factor(int P, std::vector<int> &radices)
 {
@@ -326,6 +330,11 @@ int fft_dct_exec(FftDctPlan *p, int mode, int njobs, const double *const *xs, lo
         ptrs.y[j] = ys[j];
     }
     const int P = p->P;
+    {   // compile-time specialised kernels for the hot lengths
+        const int rc = axis == 1 ? dispatch_fft_t<1>(p, mode, njobs, ptrs, ldx, n_in, ldy, n_out, batch, st)
+                                 : dispatch_fft_t<0>(p, mode, njobs, ptrs, ldx, n_in, ldy, n_out, batch, st);
+        if (rc >= 0) return rc;
+    }
     const size_t per_seq = (size_t)P * 16;
     // sequences per CTA: aim at <= ~100 KB (2 CTAs/SM); axis 0 wants >= 4 columns for full sectors
     int S = (int)((100 * 1024) / per_seq);
