@@ -201,7 +201,7 @@ class OpTimer:
                 e0.record()
                 _cabi.check(fn(*args, st))
                 e1.record()
-                self.records.append((fn.__name__, args, e0, e1))
+                self.records.append((getattr(fn, "__name__", "call"), args, e0, e1))
         torch.cuda.synchronize()
 
     def summary(self):
@@ -259,65 +259,85 @@ def run_gpu(args, cfg):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        raise SystemExit("bench.py: slab-sharded multi-GPU stepping is not implemented yet in this round "
-                         "(DESIGN.md §multi-GPU); run with --gpus 1")
     torch.cuda.set_device(local)
+    slab = world > 1
+    if slab:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        args.no_graph = True            # NCCL transposes are issued eagerly between the kernels
     from pypde_b200 import _cabi
     from pypde_b200.navier import rbc2d
 
+    def barrier():
+        torch.cuda.synchronize()
+        if slab:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if not slab:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
     t0 = time.perf_counter()
-    ns = rbc2d.NavierStokes(graph=not args.no_graph, **cfg)
+    ns = rbc2d.NavierStokes(graph=not args.no_graph, slab=slab, **cfg)
     init_state(ns, cfg["shape"])
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t0
 
-    fields = [ns.T, ns.U, ns.V, ns.pres]
     for _ in range(args.warmup):
         ns.update()
         ns.update_time()
-    torch.cuda.synchronize()
+    barrier()
+    # tensors holding the state that an end-to-end caller moves every step
+    state_tensors = ns._fast.local_state() if slab else [f.vhat for f in (ns.T, ns.U, ns.V, ns.pres)]
 
     # ---- device-resident timing -------------------------------------------------------
     sampler = ClockSampler(local)
     sampler.start()
     _cabi.launch_count_reset()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
+    barrier()
     e0.record()
     for _ in range(args.steps):
         ns.update()
         ns.update_time()
     e1.record()
-    torch.cuda.synchronize()
+    barrier()
     launches = _cabi.launch_count()
-    ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop()
+    ns.sync_fields()
     finite = bool(torch.isfinite(ns.T.vhat).all())
 
     # ---- end-to-end: host buffers in, host buffers out, every step -----------------------
-    host_in = [torch.empty(f.vhat.shape, dtype=torch.float64).pin_memory() for f in fields]
-    host_out = [torch.empty(f.vhat.shape, dtype=torch.float64).pin_memory() for f in fields]
-    for h, f in zip(host_in, fields):
-        h.copy_(f.vhat)
+    host_in = [torch.empty(t.shape, dtype=torch.float64).pin_memory() for t in state_tensors]
+    host_out = [torch.empty(t.shape, dtype=torch.float64).pin_memory() for t in state_tensors]
+    for h, t in zip(host_in, state_tensors):
+        h.copy_(t)
     h2d = sum(h.numel() * 8 for h in host_in)
     d2h = sum(h.numel() * 8 for h in host_out)
+    if slab:
+        tt = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt)
+        h2d, d2h = int(tt[0].item()), int(tt[1].item())
     e2e_steps = max(1, min(args.steps, 5))
-    torch.cuda.synchronize()
+    barrier()
     e0.record()
     for _ in range(e2e_steps):
-        for h, f in zip(host_in, fields):
-            f.vhat.copy_(h, non_blocking=True)
+        for h, t in zip(host_in, state_tensors):
+            t.copy_(h, non_blocking=True)
         ns.update()
         ns.update_time()
-        for h, f in zip(host_out, fields):
-            h.copy_(f.vhat, non_blocking=True)
+        for h, t in zip(host_out, state_tensors):
+            h.copy_(t, non_blocking=True)
         torch.cuda.synchronize()
         for hi, ho in zip(host_in, host_out):
             hi.copy_(ho)
     e1.record()
-    torch.cuda.synchronize()
-    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / e2e_steps
 
     # ---- instrumented step: per-kernel CUDA-event times, dominant kernel's roofline ----
     timer = OpTimer()
@@ -354,7 +374,7 @@ def run_gpu(args, cfg):
 
     # ---- CPU baseline: bounded sample of the same workload on rank 0 -----------------------
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and not slab and rank == 0:
         big = cfg["shape"][0] * cfg["shape"][1] > 600 * 600
         v, cpu_setup, sample = oracle_sample(cfg, 0 if big else 2)
         cpu = {"value": v, "unit": UNIT, "cores": cpu_cores(), "kind": "port", "sample": sample,
@@ -372,6 +392,7 @@ def run_gpu(args, cfg):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "shape": list(cfg["shape"]), "integrator": cfg["integrator"],
                    "dealias": cfg["dealias"], "ra": cfg["ra"], "dt": cfg["dt"], "stages_per_step": nst,
+                   "parallelism": ("slab x%d, %d all-to-all transposes per step" % (world, 10 * nst)) if slab else "single GPU",
                    "l2": "state + work arrays exceed the 126 MB L2 (no flush needed)" if N >= 1024
                    else "working set fits L2 (small-grid regime, by design of the workload)",
                    "finite": finite, "setup_s": setup_s, "cuda_graph": not args.no_graph,
@@ -391,8 +412,14 @@ def run_gpu(args, cfg):
         "kernel_ms_per_step": {k: round(v["ms"], 4) for k, v in sorted(ops_ms.items(), key=lambda kv: -kv[1]["ms"])},
         "cpu_baseline": cpu,
     }
+    if slab:
+        tms = sum(v for k, v in line["kernel_ms_per_step"].items() if k.startswith("slab_transpose"))
+        line["transpose_ms_per_step"] = tms
+        line["transpose_bytes_sent_per_rank_per_step"] = ns._fast.comm.bytes_sent // max(1, ns._fast.comm.calls // (10 * nst))
     if rank == 0:
         print(json.dumps(line))
+    if slab:
+        dist.destroy_process_group()
 
 
 def main():

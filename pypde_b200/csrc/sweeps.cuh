@@ -231,8 +231,13 @@ struct DiffDesc {
     __device__ static int len(int, int n, const SweepJob &) { return n; }
     struct State {
         double p0, p1;     // last dc of even / odd index
+        double rsc;        // RN(1 / sc): the per-element division becomes a 5-op correctly rounded sequence
     };
-    __device__ static void init(State &s, const SweepJob &, int, int) { s.p0 = s.p1 = 0.0; }
+    __device__ static void init(State &s, const SweepJob &job, int, int)
+    {
+        s.p0 = s.p1 = 0.0;
+        s.rsc = job.flag ? 1.0 / job.sc : 1.0;
+    }
     template <bool MID, class W>
     __device__ static void step(State &s, const SweepJob &job, int n, int i, const double *v, W &out)
     {
@@ -249,7 +254,7 @@ struct DiffDesc {
         }
         if (k & 1) s.p1 = cur;
         else s.p0 = cur;
-        out.st(k, job.flag ? cur / job.sc : cur);
+        out.st(k, job.flag ? div_rn_v(cur, job.sc, s.rsc, true) : cur);
     }
 };
 

@@ -35,20 +35,25 @@ class NavierStokes(NavierStokesBase, Integrator):
 
     avail_cases = ["rbc", "linear", "zero"]
 
-    def __init__(self, case="rbc", dealias_grid="fft", stepper="fast", graph=False, **kwargs):
+    def __init__(self, case="rbc", dealias_grid="fft", stepper="fast", graph=False, slab=False, **kwargs):
         """dealias_grid: "fft" (default) evaluates the 3/2-rule products on the next
         FFT-friendly Gauss-Lobatto grid >= 3N/2 (same truncated coefficients up to rounding);
         "reference" uses exactly int(3N/2) points like the reference.
         stepper: "fast" (default) runs the batched stage of fast_stepper.FastStepper,
         "reference" the operator-by-operator sequence of the reference (update_reference).
         graph: capture the whole time step in a CUDA graph (removes launch overhead on
-        small grids)."""
+        small grids).
+        slab: distribute the step over the ranks of the default torch.distributed process group
+        (one process per GPU, slab decomposition with NCCL all-to-all transposes, navier/slab.py);
+        the fields of this object then hold the replicated initial state and are refreshed by
+        sync_fields()."""
         if case not in self.avail_cases:
             raise ValueError("Specified case is not available: ", self.avail_cases)
         self.case = case
         self.dealias_grid = dealias_grid
         self._stepper_kind = stepper
         self._use_graph = graph
+        self._slab = slab
         self._fast = None
         self._graph = None
         with dealias_policy(dealias_grid):
@@ -214,14 +219,23 @@ class NavierStokes(NavierStokesBase, Integrator):
         if self._stepper_kind != "fast" or self.beta != 1.0:
             return self.update_reference()
         if self._fast is None:
-            from .fast_stepper import FastStepper
-            self._fast = FastStepper(self)
+            if self._slab:
+                from .slab_stepper import SlabStepper
+                self._fast = SlabStepper(self)
+            else:
+                from .fast_stepper import FastStepper
+                self._fast = FastStepper(self)
         if not self._use_graph:
             for rk in range(self.nstage):
                 self._fast.stage(rk)
         else:
             self._update_graph()
         self.ux, self.uz = self._fast.ux, self._fast.uz
+
+    def sync_fields(self):
+        """Slab mode: gather the distributed state into T, U, V, pres of every rank."""
+        if self._slab and self._fast is not None:
+            self._fast.gather()
 
     def _update_graph(self):
         fs = self._fast

@@ -143,6 +143,7 @@ class Plan_Poisson(_InPlacePlan):
                 dg = _diag(M, off)
                 r0 = max(0, -off)
                 dst[k, r0:r0 + dg.size] = dg
+        self._Ad, self._Cd = Ad, Cd
         self._plan = ops.PoissonPlan(Ad, Cd, np.asarray(alpha, dtype=float), singular)
 
     def _check_b(self, b):

@@ -177,3 +177,19 @@ def test_divergence_stays_small():
     div = ns.divergence_velocity(ns.U, ns.V)
     assert float(torch.linalg.norm(div)) < 1e-2
     assert torch.isfinite(ns.T.vhat).all()
+
+
+def test_slab_stepper_two_gpus():
+    """Slab decomposition over 2 GPUs (NCCL all-to-all transposes) against the oracle; skipped on
+    single-GPU boxes (the CPU side of the plumbing is covered by tests/test_slab_cpu.py)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import os
+    script = os.path.join(os.path.dirname(__file__), "dist_slab_check.py")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", script],
+                         capture_output=True, text=True, timeout=600)
+    assert "SLAB OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
