@@ -156,18 +156,18 @@ int pde_cheb_diff(const double *c, long ldc, double *dc, long lddc, int n, int b
         jobs.j[0] = make_job(c, ldc, dc, lddc, batch);
         jobs.j[0].flag = div != 1.0;
         jobs.j[0].sc = div;
-        return launch_sweep<DiffDesc>(jobs, axis, st, "pde_cheb_diff");
+        return launch_sweep<DiffDesc<false>>(jobs, axis, st, "pde_cheb_diff");
     }
     double *tmp = nullptr;
     const long n0 = axis == 0 ? n : batch, n1 = axis == 0 ? batch : n;
     PDE_CUDA(cudaMallocAsync(&tmp, sizeof(double) * n0 * n1, st));
     jobs.j[0] = make_job(c, ldc, tmp, n1, batch);
-    int rc = launch_sweep<DiffDesc>(jobs, axis, st, "pde_cheb_diff(1/2)");
+    int rc = launch_sweep<DiffDesc<false>>(jobs, axis, st, "pde_cheb_diff(1/2)");
     if (rc == PDE_OK) {
         jobs.j[0] = make_job(tmp, n1, dc, lddc, batch);
         jobs.j[0].flag = div != 1.0;
         jobs.j[0].sc = div;
-        rc = launch_sweep<DiffDesc>(jobs, axis, st, "pde_cheb_diff(2/2)");
+        rc = launch_sweep<DiffDesc<false>>(jobs, axis, st, "pde_cheb_diff(2/2)");
     }
     cudaFreeAsync(tmp, st);
     return rc;
@@ -186,12 +186,12 @@ static int tdma_run(const double *s, const double *a, const double *den, const d
     jobs.j[0].tab[1] = a;
     jobs.j[0].tab[2] = den;
     jobs.j[0].tab[3] = w;
-    int rc = launch_sweep<TdmaFwd>(jobs, axis, st, what);
+    int rc = launch_sweep<TdmaFwd<false>>(jobs, axis, st, what);
     if (rc != PDE_OK) return rc;
     jobs.j[0].in[0] = x;
     jobs.j[0].ldin[0] = ldx;
     jobs.j[0].in[1] = nullptr;
-    return launch_sweep<TdmaBwd>(jobs, axis, st, what);
+    return launch_sweep<TdmaBwd<false>>(jobs, axis, st, what);
 }
 
 int pde_tdma2_solve(const double *a, const double *den, const double *w, const double *d, long ldd,
@@ -226,9 +226,9 @@ int pde_fdma_solve(const double *l, const double *d, const double *u1, const dou
     jobs.j[0].tab[1] = d;
     jobs.j[0].tab[2] = u1;
     jobs.j[0].tab[3] = u2;
-    int rc = launch_sweep<FdmaFwd>(jobs, axis, as_stream(stream), "pde_fdma_solve(fwd)");
+    int rc = launch_sweep<FdmaFwd<false>>(jobs, axis, as_stream(stream), "pde_fdma_solve(fwd)");
     if (rc != PDE_OK) return rc;
-    return launch_sweep<FdmaBwd>(jobs, axis, as_stream(stream), "pde_fdma_solve(bwd)");
+    return launch_sweep<FdmaBwd<false>>(jobs, axis, as_stream(stream), "pde_fdma_solve(bwd)");
 }
 
 int pde_twodma_solve(const double *d, const double *u, double *x, long ldx, int n, int batch, int axis,
@@ -243,7 +243,7 @@ int pde_twodma_solve(const double *d, const double *u, double *x, long ldx, int 
     jobs.j[0] = make_job(x, ldx, x, ldx, batch);
     jobs.j[0].tab[0] = d;
     jobs.j[0].tab[1] = u;
-    return launch_sweep<TwodmaBwd>(jobs, axis, as_stream(stream), "pde_twodma_solve");
+    return launch_sweep<TwodmaBwd<false>>(jobs, axis, as_stream(stream), "pde_twodma_solve");
 }
 
 int pde_to_cheb(const double *s, const double *v, long ldv, int M, double *u, long ldu, int n_out,
@@ -340,14 +340,14 @@ int pde_poisson_solve(pde_poisson_plan_t p, double *x, long ldx, void *stream)
     jobs.j[0].itab = p->t.off;
     jobs.j[0].in[1] = p->t.l;
     jobs.j[0].ldin[1] = p->m;
-    int rc = launch_sweep<PoissonFwd>(jobs, 0, as_stream(stream), "pde_poisson_solve(fwd)");
+    int rc = launch_sweep<PoissonFwd<true>>(jobs, 0, as_stream(stream), "pde_poisson_solve(fwd)");
     if (rc != PDE_OK) return rc;
     jobs.j[0].in[1] = p->t.d;
     jobs.j[0].in[2] = p->t.u1;
     jobs.j[0].in[3] = p->t.u2;
     jobs.j[0].in[4] = p->t.rd;
     jobs.j[0].ldin[1] = jobs.j[0].ldin[2] = jobs.j[0].ldin[3] = jobs.j[0].ldin[4] = p->m;
-    return launch_sweep<PoissonBwd>(jobs, 0, as_stream(stream), "pde_poisson_solve(bwd)");
+    return launch_sweep<PoissonBwd<true>>(jobs, 0, as_stream(stream), "pde_poisson_solve(bwd)");
 }
 
 int pde_transpose(const double *in, long ldin, double *out, long ldout, int n0, int n1, void *stream)

@@ -116,15 +116,28 @@ int pde_sweep(int op, int axis, int n, int njobs, const pde_sweep_job *jobs, voi
     sj.n = n;
     for (int j = 0; j < njobs; ++j) sj.j[j] = jobs[j];
     cudaStream_t st = as_stream(stream);
+    // FULL instantiations (no run-time feature tests) when every job supplies all optional tables
+    bool full = true;
+    for (int j = 0; j < njobs; ++j) {
+        const pde_sweep_job &jb = jobs[j];
+        switch (op) {
+        case PDE_SWEEP_DIFF: full = full && jb.flag != 0; break;
+        case PDE_SWEEP_TDMA_FWD: full = full && jb.tab[0] && jb.tab[4] && jb.in[1]; break;
+        case PDE_SWEEP_FDMA_BWD: full = full && jb.tab[4]; break;
+        default: break;
+        }
+    }
+#define PDE_SW(OP, what) (full ? launch_sweep<OP<true>>(sj, axis, st, what) : launch_sweep<OP<false>>(sj, axis, st, what))
     switch (op) {
-    case PDE_SWEEP_DIFF: return launch_sweep<DiffDesc>(sj, axis, st, "pde_sweep(diff)");
-    case PDE_SWEEP_TDMA_FWD: return launch_sweep<TdmaFwd>(sj, axis, st, "pde_sweep(tdma fwd)");
-    case PDE_SWEEP_TDMA_BWD: return launch_sweep<TdmaBwd>(sj, axis, st, "pde_sweep(tdma bwd)");
-    case PDE_SWEEP_FDMA_FWD: return launch_sweep<FdmaFwd>(sj, axis, st, "pde_sweep(fdma fwd)");
-    case PDE_SWEEP_FDMA_BWD: return launch_sweep<FdmaBwd>(sj, axis, st, "pde_sweep(fdma bwd)");
-    case PDE_SWEEP_TWODMA_BWD: return launch_sweep<TwodmaBwd>(sj, axis, st, "pde_sweep(twodma)");
+    case PDE_SWEEP_DIFF: return PDE_SW(DiffDesc, "pde_sweep(diff)");
+    case PDE_SWEEP_TDMA_FWD: return PDE_SW(TdmaFwd, "pde_sweep(tdma fwd)");
+    case PDE_SWEEP_TDMA_BWD: return launch_sweep<TdmaBwd<true>>(sj, axis, st, "pde_sweep(tdma bwd)");
+    case PDE_SWEEP_FDMA_FWD: return launch_sweep<FdmaFwd<true>>(sj, axis, st, "pde_sweep(fdma fwd)");
+    case PDE_SWEEP_FDMA_BWD: return PDE_SW(FdmaBwd, "pde_sweep(fdma bwd)");
+    case PDE_SWEEP_TWODMA_BWD: return launch_sweep<TwodmaBwd<false>>(sj, axis, st, "pde_sweep(twodma)");
     default: set_error("pde_sweep: unknown op %d", op); return PDE_ERR_ARG;
     }
+#undef PDE_SW
 }
 
 int pde_to_cheb_multi(int axis, int njobs, const pde_stencil_job *jobs, void *stream)

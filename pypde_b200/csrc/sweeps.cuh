@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(BD) k_sweep(SweepJobs jobs)
     extern __shared__ double ring[];
     const SweepJob &job = jobs.j[blockIdx.y];
     const int q = blockIdx.x * BD + threadIdx.x;
-    if (q >= job.nseq) return;
+    if (blockIdx.x * BD >= job.nseq) return;          // whole CTA beyond this job's sequences
     const int n = jobs.n;
     double *my = ring + threadIdx.x;
     constexpr int NIN = Op::NIN;
@@ -106,6 +106,7 @@ __global__ void __launch_bounds__(BD) k_sweep(SweepJobs jobs)
     const int np = (n - par + 1) / 2;                 // chain length
     if (np <= 0) return;
     const int top = par + 2 * (np - 1);
+    const bool active = q < job.nseq;                 // inactive lanes only help staging the tables
 
     // per-stream base pointer of this sequence and element stride (in doubles)
     const double *gq[NIN];
@@ -150,8 +151,29 @@ __global__ void __launch_bounds__(BD) k_sweep(SweepJobs jobs)
         }
     };
 
+    // Per-index coefficient tables: the parity half this CTA walks is staged once in shared memory
+    // (entry t <-> index par + 2t).  __ldg table reads were the top stall of the first version (ncu:
+    // long_scoreboard 9-13 per issue, L1 hit rate 4-50 % because the cp.async stream evicts them).
+    constexpr int NT = Op::NT;
+    const int H = (n + 1) / 2 + 2;
+    double *tsm = ring + RING_K * NIN * BD;
+    if (NT > 0) {
+#pragma unroll
+        for (int k = 0; k < NT; ++k) {
+            const double *tp = job.tab[Op::tab_index(k)];
+            const int tl = Op::tab_len(k, n);
+            for (int t = threadIdx.x; t < H; t += BD) {
+                const int i = par + 2 * t;
+                tsm[k * H + t] = (tp != nullptr && i < tl) ? __ldg(tp + i) : 0.0;
+            }
+        }
+        __syncwarp();
+    }
+    if (!active) return;
     typename Op::State st;
     Op::init(st, job, n, q);
+    st.tsm = tsm;
+    st.H = H;
     const int nchunks = (np + C - 1) / C;
     // chunks [c_lo, c_hi) are "interior": full, every stream index valid, no edge logic in Op::step
     // (all their steps satisfy 8 <= i <= n-9)
@@ -222,47 +244,64 @@ __global__ void __launch_bounds__(BD) k_sweep(SweepJobs jobs)
 // operators
 // ---------------------------------------------------------------------------
 
+// Every operator is templated on FULL: the batched stepper supplies every optional table
+// (stencil, reciprocals, scale), so the FULL instantiation has no run-time feature tests; the
+// generic C-ABI entry points use FULL = false.  A thread walks ONE parity chain, so the
+// recurrence state is a single value.  Per-index tables are read from the shared-memory copy
+// staged by k_sweep: table k, index i  ->  tsm[k*H + (i >> 1)]  (i has the chain's parity).
+#define PDE_TB(st, k, i) ((st).tsm[(k) * (st).H + ((i) >> 1)])
+
 // differentiate_cheby.f90:28-53: dc[n-1] = 0, dc[n-2] = 2(n-1)c[n-1], dc[k] = dc[k+2] + 2(k+1)c[k+1],
 // dc[0] = dc[2]/2 + c[1]; stored value divided by job.sc when job.flag (grad(): /= scale**deriv).
+template <bool FULL>
 struct DiffDesc {
     static constexpr int NIN = 1;
+    static constexpr int NT = 0;
     static constexpr bool ASC = false;
     __device__ static int off(int) { return 0; }
     __device__ static int len(int, int n, const SweepJob &) { return n; }
+    __device__ static int tab_index(int) { return 0; }
+    __device__ static int tab_len(int, int) { return 0; }
     struct State {
-        double p0, p1;     // last dc of even / odd index
-        double rsc;        // RN(1 / sc): the per-element division becomes a 5-op correctly rounded sequence
+        const double *tsm;
+        int H;
+        double p;          // dc[k+2] of this chain
+        double sc, rsc;    // scale and RN(1/scale): the division is a 5-op correctly rounded sequence
+        bool div;
     };
     __device__ static void init(State &s, const SweepJob &job, int, int)
     {
-        s.p0 = s.p1 = 0.0;
-        s.rsc = job.flag ? 1.0 / job.sc : 1.0;
+        s.p = 0.0;
+        s.div = FULL ? true : job.flag != 0;
+        s.sc = job.sc;
+        s.rsc = 1.0 / job.sc;
     }
     template <bool MID, class W>
-    __device__ static void step(State &s, const SweepJob &job, int n, int i, const double *v, W &out)
+    __device__ static void step(State &s, const SweepJob &, int n, int i, const double *v, W &out)
     {
         const int k = i - 1;
         double cur;
         if (MID) {
-            cur = ((k & 1) ? s.p1 : s.p0) + (double)(2 * i) * v[0];
+            cur = s.p + (double)(2 * i) * v[0];
         } else {
             if (i == n - 1) out.st(n - 1, 0.0);
             if (i == 0) return;
             if (i == n - 1) cur = (double)(2 * (n - 1)) * v[0];
-            else if (k >= 1) cur = ((k & 1) ? s.p1 : s.p0) + (double)(2 * i) * v[0];
-            else cur = s.p0 / 2.0 + v[0];
+            else if (k >= 1) cur = s.p + (double)(2 * i) * v[0];
+            else cur = s.p / 2.0 + v[0];
         }
-        if (k & 1) s.p1 = cur;
-        else s.p0 = cur;
-        out.st(k, job.flag ? div_rn_v(cur, job.sc, s.rsc, true) : cur);
+        s.p = cur;
+        out.st(k, s.div ? div_rn_v(cur, s.sc, s.rsc, true) : cur);
     }
 };
 
 // tdma.f90:55-106, k = 2, forward part: g_i = (rhs_i - a_{i-2} g_{i-2}) / den_i with the fused
 // S^T product rhs_i = u_i + s_i u_{i+2} (chebyshev.py:327) when tab[0] = s is given.
-// tab: 0 = s (or null), 1 = a, 2 = den, 3 = w (back substitution), 4 = RN(1/den) (optional).
+// job.tab: 0 = s (or null), 1 = a, 2 = den, 3 = w (back substitution), 4 = RN(1/den) (optional).
+template <bool FULL>
 struct TdmaFwd {
     static constexpr int NIN = 2;
+    static constexpr int NT = 4;          // staged: 0 = s, 1 = a, 2 = den, 3 = rden
     static constexpr bool ASC = true;
     __device__ static int off(int s) { return s == 0 ? 0 : 2; }
     __device__ static int len(int s, int n, const SweepJob &job)
@@ -270,137 +309,178 @@ struct TdmaFwd {
         if (s == 0) return n;
         return job.tab[0] ? n + 2 : 0;
     }
+    __device__ static int tab_index(int k) { return k == 3 ? 4 : k; }
+    __device__ static int tab_len(int k, int n) { return k == 1 ? n - 2 : n; }
     struct State {
-        double g0, g1;
+        const double *tsm;
+        int H;
+        double g;
+        bool has_s, has_r;
     };
-    __device__ static void init(State &s, const SweepJob &, int, int) { s.g0 = s.g1 = 0.0; }
+    __device__ static void init(State &s, const SweepJob &job, int, int)
+    {
+        s.g = 0.0;
+        s.has_s = FULL || job.tab[0] != nullptr;
+        s.has_r = FULL || job.tab[4] != nullptr;
+    }
     template <bool MID, class W>
-    __device__ static void step(State &s, const SweepJob &job, int n, int i, const double *v, W &out)
+    __device__ static void step(State &s, const SweepJob &, int, int i, const double *v, W &out)
     {
         double rhs = v[0];
-        if (job.tab[0]) rhs = v[0] + __ldg(job.tab[0] + i) * v[1];
+        if (s.has_s) rhs = v[0] + PDE_TB(s, 0, i) * v[1];
+        const double den = PDE_TB(s, 2, i);
         double g;
-        if (!MID && i < 2) g = rhs / __ldg(job.tab[2] + i);
-        else g = div_rn(rhs - __ldg(job.tab[1] + i - 2) * ((i & 1) ? s.g1 : s.g0), __ldg(job.tab[2] + i), job.tab[4], i);
-        if (i & 1) s.g1 = g;
-        else s.g0 = g;
+        if (!MID && i < 2) g = rhs / den;
+        else g = div_rn_v(rhs - PDE_TB(s, 1, i - 2) * s.g, den, PDE_TB(s, 3, i), s.has_r);
+        s.g = g;
         out.st(i, g);
     }
 };
 
-// back substitution x_i = g_i - w_i x_{i+2} (in place), tab[3] = w
+// back substitution x_i = g_i - w_i x_{i+2} (in place), job.tab[3] = w
+template <bool FULL>
 struct TdmaBwd {
     static constexpr int NIN = 1;
+    static constexpr int NT = 1;
     static constexpr bool ASC = false;
     __device__ static int off(int) { return 0; }
     __device__ static int len(int, int n, const SweepJob &) { return n; }
+    __device__ static int tab_index(int) { return 3; }
+    __device__ static int tab_len(int, int n) { return n - 2; }
     struct State {
-        double x0, x1;
+        const double *tsm;
+        int H;
+        double x;
     };
-    __device__ static void init(State &s, const SweepJob &, int, int) { s.x0 = s.x1 = 0.0; }
+    __device__ static void init(State &s, const SweepJob &, int, int) { s.x = 0.0; }
     template <bool MID, class W>
-    __device__ static void step(State &s, const SweepJob &job, int n, int i, const double *v, W &out)
+    __device__ static void step(State &s, const SweepJob &, int n, int i, const double *v, W &out)
     {
         double x = v[0];
         if (MID || i < n - 2) {
-            x = v[0] - __ldg(job.tab[3] + i) * ((i & 1) ? s.x1 : s.x0);
+            x = v[0] - PDE_TB(s, 0, i) * s.x;
             out.st(i, x);
         }
-        if (i & 1) s.x1 = x;
-        else s.x0 = x;
+        s.x = x;
     }
 };
 
-// fdma.f90:26-36: forward x_i -= l_{i-2} x_{i-2}; tab: 0 = l, 1 = d, 2 = u1, 3 = u2, 4 = RN(1/d) (optional)
+// fdma.f90:26-36: forward x_i -= l_{i-2} x_{i-2}; job.tab: 0 = l, 1 = d, 2 = u1, 3 = u2, 4 = RN(1/d) (optional)
+template <bool FULL>
 struct FdmaFwd {
     static constexpr int NIN = 1;
+    static constexpr int NT = 1;
     static constexpr bool ASC = true;
     __device__ static int off(int) { return 0; }
     __device__ static int len(int, int n, const SweepJob &) { return n; }
+    __device__ static int tab_index(int) { return 0; }
+    __device__ static int tab_len(int, int n) { return n - 2; }
     struct State {
-        double p0, p1;
+        const double *tsm;
+        int H;
+        double p;
     };
-    __device__ static void init(State &s, const SweepJob &, int, int) { s.p0 = s.p1 = 0.0; }
+    __device__ static void init(State &s, const SweepJob &, int, int) { s.p = 0.0; }
     template <bool MID, class W>
-    __device__ static void step(State &s, const SweepJob &job, int, int i, const double *v, W &out)
+    __device__ static void step(State &s, const SweepJob &, int, int i, const double *v, W &out)
     {
         double x = v[0];
         if (MID || i >= 2) {
-            x = v[0] - __ldg(job.tab[0] + i - 2) * ((i & 1) ? s.p1 : s.p0);
+            x = v[0] - PDE_TB(s, 0, i - 2) * s.p;
             out.st(i, x);
         }
-        if (i & 1) s.p1 = x;
-        else s.p0 = x;
+        s.p = x;
     }
 };
 
+template <bool FULL>
 struct FdmaBwd {
     static constexpr int NIN = 1;
+    static constexpr int NT = 4;          // staged: 0 = d, 1 = u1, 2 = u2, 3 = rd
     static constexpr bool ASC = false;
     __device__ static int off(int) { return 0; }
     __device__ static int len(int, int n, const SweepJob &) { return n; }
+    __device__ static int tab_index(int k) { return k + 1; }
+    __device__ static int tab_len(int k, int n) { return k == 1 ? n - 2 : (k == 2 ? n - 4 : n); }
     struct State {
-        double a2, a4, b2, b4;     // x_{i+2}, x_{i+4} of the even (a) / odd (b) chain
+        const double *tsm;
+        int H;
+        double x2, x4;     // x_{i+2}, x_{i+4} of this chain
+        bool has_r;
     };
-    __device__ static void init(State &s, const SweepJob &, int, int) { s.a2 = s.a4 = s.b2 = s.b4 = 0.0; }
-    template <bool MID, class W>
-    __device__ static void step(State &s, const SweepJob &job, int n, int i, const double *v, W &out)
+    __device__ static void init(State &s, const SweepJob &job, int, int)
     {
-        const double x2 = (i & 1) ? s.b2 : s.a2, x4 = (i & 1) ? s.b4 : s.a4;
-        const double d = __ldg(job.tab[1] + i);
+        s.x2 = s.x4 = 0.0;
+        s.has_r = FULL || job.tab[4] != nullptr;
+    }
+    template <bool MID, class W>
+    __device__ static void step(State &s, const SweepJob &, int n, int i, const double *v, W &out)
+    {
+        const double d = PDE_TB(s, 0, i);
         double x;
         if (!MID && i >= n - 2) x = v[0] / d;
-        else if (!MID && i >= n - 4) x = (v[0] - __ldg(job.tab[2] + i) * x2) / d;
-        else x = div_rn(v[0] - __ldg(job.tab[2] + i) * x2 - __ldg(job.tab[3] + i) * x4, d, job.tab[4], i);
+        else if (!MID && i >= n - 4) x = (v[0] - PDE_TB(s, 1, i) * s.x2) / d;
+        else x = div_rn_v(v[0] - PDE_TB(s, 1, i) * s.x2 - PDE_TB(s, 2, i) * s.x4, d, PDE_TB(s, 3, i), s.has_r);
         out.st(i, x);
-        if (i & 1) {
-            s.b4 = s.b2;
-            s.b2 = x;
-        } else {
-            s.a4 = s.a2;
-            s.a2 = x;
-        }
+        s.x4 = s.x2;
+        s.x2 = x;
     }
 };
 
-// twodma.f90:17-22; tab: 0 = d, 1 = u
+// twodma.f90:17-22; job.tab: 0 = d, 1 = u, 4 = RN(1/d) (optional)
+template <bool FULL>
 struct TwodmaBwd {
     static constexpr int NIN = 1;
+    static constexpr int NT = 3;          // staged: 0 = d, 1 = u, 2 = rd
     static constexpr bool ASC = false;
     __device__ static int off(int) { return 0; }
     __device__ static int len(int, int n, const SweepJob &) { return n; }
+    __device__ static int tab_index(int k) { return k == 2 ? 4 : k; }
+    __device__ static int tab_len(int k, int n) { return k == 1 ? n - 2 : n; }
     struct State {
-        double x0, x1;
+        const double *tsm;
+        int H;
+        double x;
+        bool has_r;
     };
-    __device__ static void init(State &s, const SweepJob &, int, int) { s.x0 = s.x1 = 0.0; }
-    template <bool MID, class W>
-    __device__ static void step(State &s, const SweepJob &job, int n, int i, const double *v, W &out)
+    __device__ static void init(State &s, const SweepJob &job, int, int)
     {
-        const double d = __ldg(job.tab[0] + i);
+        s.x = 0.0;
+        s.has_r = job.tab[4] != nullptr;
+    }
+    template <bool MID, class W>
+    __device__ static void step(State &s, const SweepJob &, int n, int i, const double *v, W &out)
+    {
+        const double d = PDE_TB(s, 0, i);
         double x;
         if (!MID && i >= n - 2) x = v[0] / d;
-        else x = div_rn(v[0] - __ldg(job.tab[1] + i) * ((i & 1) ? s.x1 : s.x0), d, job.tab[4], i);
+        else x = div_rn_v(v[0] - PDE_TB(s, 1, i) * s.x, d, PDE_TB(s, 2, i), s.has_r);
         out.st(i, x);
-        if (i & 1) s.x1 = x;
-        else s.x0 = x;
+        s.x = x;
     }
 };
 
 // Poisson (A + lam_q C) columns with per-column LU tables (n x m arrays, same layout as x):
 // streams: 0 = x, 1 = L (read at i-2);  itab[q] = 1 where the singular branch drops row/col 0
 // (fdma.f90:173-185): that column's system starts at i = 1 and x[0] = 0.
+template <bool FULL>
 struct PoissonFwd {
     static constexpr int NIN = 2;
+    static constexpr int NT = 0;
     static constexpr bool ASC = true;
     __device__ static int off(int s) { return s == 0 ? 0 : -2; }
     __device__ static int len(int, int n, const SweepJob &) { return n; }
+    __device__ static int tab_index(int) { return 0; }
+    __device__ static int tab_len(int, int) { return 0; }
     struct State {
-        double p0, p1;
+        const double *tsm;
+        int H;
+        double p;
         int off;
     };
     __device__ static void init(State &s, const SweepJob &job, int, int q)
     {
-        s.p0 = s.p1 = 0.0;
+        s.p = 0.0;
         s.off = job.itab[q];
     }
     template <bool MID, class W>
@@ -412,46 +492,45 @@ struct PoissonFwd {
         }
         double x = v[0];
         if (MID || i >= s.off + 2) {
-            x = v[0] - v[1] * ((i & 1) ? s.p1 : s.p0);
+            x = v[0] - v[1] * s.p;
             out.st(i, x);
         }
-        if (i & 1) s.p1 = x;
-        else s.p0 = x;
+        s.p = x;
     }
 };
 
-// streams: 0 = x, 1 = D, 2 = U1, 3 = U2, 4 = RN(1/D) (optional)
+// streams: 0 = x, 1 = D, 2 = U1, 3 = U2, 4 = RN(1/D)
+template <bool FULL>
 struct PoissonBwd {
     static constexpr int NIN = 5;
+    static constexpr int NT = 0;
     static constexpr bool ASC = false;
     __device__ static int off(int) { return 0; }
     __device__ static int len(int, int n, const SweepJob &) { return n; }
+    __device__ static int tab_index(int) { return 0; }
+    __device__ static int tab_len(int, int) { return 0; }
     struct State {
-        double a2, a4, b2, b4;
+        const double *tsm;
+        int H;
+        double x2, x4;
         int off;
     };
     __device__ static void init(State &s, const SweepJob &job, int, int q)
     {
-        s.a2 = s.a4 = s.b2 = s.b4 = 0.0;
+        s.x2 = s.x4 = 0.0;
         s.off = job.itab[q];
     }
     template <bool MID, class W>
-    __device__ static void step(State &s, const SweepJob &job, int n, int i, const double *v, W &out)
+    __device__ static void step(State &s, const SweepJob &, int n, int i, const double *v, W &out)
     {
         if (!MID && i < s.off) return;
-        const double x2 = (i & 1) ? s.b2 : s.a2, x4 = (i & 1) ? s.b4 : s.a4;
         double x;
         if (!MID && i >= n - 2) x = v[0] / v[1];
-        else if (!MID && i >= n - 4) x = (v[0] - v[2] * x2) / v[1];
-        else x = div_rn_v(v[0] - v[2] * x2 - v[3] * x4, v[1], v[4], job.in[4] != nullptr);
+        else if (!MID && i >= n - 4) x = (v[0] - v[2] * s.x2) / v[1];
+        else x = div_rn_v(v[0] - v[2] * s.x2 - v[3] * s.x4, v[1], v[4], true);
         out.st(i, x);
-        if (i & 1) {
-            s.b4 = s.b2;
-            s.b2 = x;
-        } else {
-            s.a4 = s.a2;
-            s.a2 = x;
-        }
+        s.x4 = s.x2;
+        s.x2 = x;
     }
 };
 
@@ -464,9 +543,26 @@ static int launch_sweep(const SweepJobs &jobs, int axis, cudaStream_t st, const 
     if (maxseq <= 0) return PDE_OK;
     constexpr int BD = 32;      // one warp per CTA: spreads the few thousand chains over all SMs
     dim3 grid(ceil_div(maxseq, BD), jobs.njobs, 2);      // z = parity chain
-    const size_t smem = (size_t)RING_K * Op::NIN * BD * sizeof(double);
-    if (axis == 0) k_sweep<Op, true, BD><<<grid, BD, smem, st>>>(jobs);
-    else k_sweep<Op, false, BD><<<grid, BD, smem, st>>>(jobs);
+    const int H = (jobs.n + 1) / 2 + 2;
+    const size_t smem = ((size_t)RING_K * Op::NIN * BD + (size_t)Op::NT * H) * sizeof(double);
+    if (smem > 200 * 1024) {
+        set_error("%s: sequence length %d needs %zu bytes of shared memory", what, jobs.n, smem);
+        return PDE_ERR_UNSUPPORTED;
+    }
+    static size_t attr_lc = 0, attr_ts = 0;
+    if (axis == 0) {
+        if (smem > 48 * 1024 && smem > attr_lc) {
+            PDE_CUDA(cudaFuncSetAttribute(k_sweep<Op, true, BD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_lc = 200 * 1024;
+        }
+        k_sweep<Op, true, BD><<<grid, BD, smem, st>>>(jobs);
+    } else {
+        if (smem > 48 * 1024 && smem > attr_ts) {
+            PDE_CUDA(cudaFuncSetAttribute(k_sweep<Op, false, BD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            attr_ts = 200 * 1024;
+        }
+        k_sweep<Op, false, BD><<<grid, BD, smem, st>>>(jobs);
+    }
     return after_launch(what);
 }
 
