@@ -249,7 +249,7 @@ static int launch_fft_t(const FftDctPlan *p, int mode, int njobs, const DctPtrs 
     if (!attr) {
         // enough shared memory for 4 CTAs (or as many as fit), the rest stays L1 for the twiddle table
         {
-            const int want = (int)(smem + 1024) * 4;
+            const int want = (int)(smem + 1024) * 3;
             const int pct = want >= 227 * 1024 ? 100 : (want * 100 + 227 * 1024 - 1) / (227 * 1024);
             cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
         }

@@ -30,6 +30,10 @@ class SlabStepper(FastStepper):
         FastStepper.__init__(self, ns)
 
     # ------------------------------------------------------------------ layout helpers
+    def _new(self, *shape):
+        # bundles are exchanged as flat buffers: always contiguous (no pitch padding)
+        return torch.zeros(shape, dtype=torch.float64, device=self.dev)
+
     def _alloc(self):
         N0, N1, M0, M1, D0, D1 = self.N0, self.N1, self.M0, self.M1, self.D0, self.D1
         P, r = self.P, self.r
