@@ -15,12 +15,12 @@
 
 namespace pde {
 
-constexpr int BM = 128, BN = 64, BK = 16, STAGES = 3;
+constexpr int BN = 64, BK = 16, STAGES = 3;   // BM = 32 * MI (MI m-tiles of 8 rows per warp, 4 warps along M)
 constexpr int APITCH = BK + 4;           // doubles per smem row of an (rows x BK) tile
 constexpr int BPITCH_NN = BN + 4;        // doubles per smem row of the (BK x BN) tile
-constexpr int A_TILE = BM * APITCH;      // doubles
+constexpr int A_TILE_MAX = 128 * APITCH;      // doubles
 constexpr int B_TILE = (BN * APITCH > BK * BPITCH_NN) ? BN * APITCH : BK * BPITCH_NN;
-constexpr int GEMM_SMEM = STAGES * (A_TILE + B_TILE) * 8;
+constexpr int GEMM_SMEM = STAGES * (A_TILE_MAX + B_TILE) * 8;
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes)
 {
@@ -101,11 +101,13 @@ __device__ __forceinline__ void load_tile_nmajor(double *sm, const double *g, lo
     }
 }
 
-template <bool TB, bool VEC>
+template <bool TB, bool VEC, int MI>
 __global__ void __launch_bounds__(256, 2)
 k_gemm_f64(const double *__restrict__ A, long lda, const double *__restrict__ B, long ldb,
            double *__restrict__ C, long ldc, int M, int N, int K)
 {
+    constexpr int BM = 32 * MI;
+    constexpr int A_TILE = BM * APITCH;
     extern __shared__ __align__(16) double smem[];
     double *As = smem;
     double *Bs = smem + STAGES * A_TILE;
@@ -114,9 +116,9 @@ k_gemm_f64(const double *__restrict__ A, long lda, const double *__restrict__ B,
     const int wm = warp & 3, wn = warp >> 2;
     const int lr = lane >> 2, lc = lane & 3;
 
-    double acc[4][4][2];
+    double acc[MI][4][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
@@ -137,19 +139,19 @@ k_gemm_f64(const double *__restrict__ A, long lda, const double *__restrict__ B,
         const int nk = kt + STAGES - 1;
         if (nk < KT) load(nk, nk % STAGES);
         cp_async_commit();
-        const double *as = As + (kt % STAGES) * A_TILE + (wm * 32 + lr) * APITCH + lc;
+        const double *as = As + (kt % STAGES) * A_TILE + (wm * 8 * MI + lr) * APITCH + lc;
         const double *bs = TB ? Bs + (kt % STAGES) * B_TILE + (wn * 32 + lr) * APITCH + lc
                               : Bs + (kt % STAGES) * B_TILE + lc * BPITCH_NN + wn * 32 + lr;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
-            double a[4], b[4];
+            double a[MI], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = as[i * 8 * APITCH + kk * 4];
+            for (int i = 0; i < MI; ++i) a[i] = as[i * 8 * APITCH + kk * 4];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 b[j] = TB ? bs[j * 8 * APITCH + kk * 4] : bs[kk * 4 * BPITCH_NN + j * 8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < MI; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
@@ -157,8 +159,8 @@ k_gemm_f64(const double *__restrict__ A, long lda, const double *__restrict__ B,
     cp_async_wait<0>();
 
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int row = m0 + wm * 32 + i * 8 + lr;
+    for (int i = 0; i < MI; ++i) {
+        const int row = m0 + wm * 8 * MI + i * 8 + lr;
         if (row >= M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -180,22 +182,43 @@ int gemm_f64(bool transB, const double *A, long lda, const double *B, long ldb, 
     if (m <= 0 || n <= 0) return PDE_OK;
     const bool vec = (lda % 2 == 0) && (ldb % 2 == 0) && (ldc % 2 == 0) &&
                      ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0);
-    dim3 grid(ceil_div(n, BN), ceil_div(m, BM));
+    // CTA tile 128 x 64 when that fills the machine, else 64 x 64 / 32 x 64 (row slabs of the
+    // multi-GPU path and small grids have few rows)
+    const int sms = sm_count();
+    int MI = 4;
+    if ((long)ceil_div(n, BN) * ceil_div(m, 128) < 2L * sms) MI = 2;
+    if ((long)ceil_div(n, BN) * ceil_div(m, 64) < 2L * sms) MI = 1;
+    dim3 grid(ceil_div(n, BN), ceil_div(m, 32 * MI));
     static bool attr = false;
+    auto set_attr = [&](auto kern) {
+        return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    };
     if (!attr) {
-        PDE_CUDA(cudaFuncSetAttribute(k_gemm_f64<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-        PDE_CUDA(cudaFuncSetAttribute(k_gemm_f64<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-        PDE_CUDA(cudaFuncSetAttribute(k_gemm_f64<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-        PDE_CUDA(cudaFuncSetAttribute(k_gemm_f64<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+#define PDE_GEMM_ATTR(TBV, VECV)                                  \
+        PDE_CUDA(set_attr(k_gemm_f64<TBV, VECV, 4>));               \
+        PDE_CUDA(set_attr(k_gemm_f64<TBV, VECV, 2>));               \
+        PDE_CUDA(set_attr(k_gemm_f64<TBV, VECV, 1>));
+        PDE_GEMM_ATTR(false, false)
+        PDE_GEMM_ATTR(false, true)
+        PDE_GEMM_ATTR(true, false)
+        PDE_GEMM_ATTR(true, true)
+#undef PDE_GEMM_ATTR
         attr = true;
     }
+#define PDE_GEMM_LAUNCH(TBV, VECV)                                                                              \
+    do {                                                                                                        \
+        if (MI == 4) k_gemm_f64<TBV, VECV, 4><<<grid, 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, m, n, k);   \
+        else if (MI == 2) k_gemm_f64<TBV, VECV, 2><<<grid, 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, m, n, k); \
+        else k_gemm_f64<TBV, VECV, 1><<<grid, 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, m, n, k);           \
+    } while (0)
     if (transB) {
-        if (vec) k_gemm_f64<true, true><<<grid, 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, m, n, k);
-        else k_gemm_f64<true, false><<<grid, 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, m, n, k);
+        if (vec) PDE_GEMM_LAUNCH(true, true);
+        else PDE_GEMM_LAUNCH(true, false);
     } else {
-        if (vec) k_gemm_f64<false, true><<<grid, 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, m, n, k);
-        else k_gemm_f64<false, false><<<grid, 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, m, n, k);
+        if (vec) PDE_GEMM_LAUNCH(false, true);
+        else PDE_GEMM_LAUNCH(false, false);
     }
+#undef PDE_GEMM_LAUNCH
     return after_launch("pde_gemm_f64");
 }
 
