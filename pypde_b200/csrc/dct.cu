@@ -96,7 +96,10 @@ int pde_dct_plan_create(pde_dct_plan_t *plan, int L, int algo)
     if (algo == 0) {
         // FFT whenever L-1 is even and smooth (specialised kernels exist from P = 96 on); the dense
         // DMMA matrix for very short or awkward lengths
-        algo = (L >= 49 && fft_dct_supported(L)) ? fft_dct_supported(L) : 1;
+        // (3: Bluestein pays off from L ~ 512 on; below, the dense matrix is faster)
+        const int sup = fft_dct_supported(L);
+        // measured (profiles/r01_dct_sweep.json): dense 1.8 TB/s at L = 128, 0.97 TB/s at 256; FFT ~0.85 TB/s
+        algo = (sup == 2 && L >= 320) ? 2 : ((sup == 3 && L >= 384) ? 3 : 1);
     }
     pde_dct_plan_s *p = new pde_dct_plan_s();
     p->L = L;

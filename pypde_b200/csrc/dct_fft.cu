@@ -28,9 +28,11 @@ struct FftDctPlan {
     int L = 0, P = 0;
     int npass = 0;
     int radix[24];
-    double2 *W = nullptr;     // W[j]  = exp(-2 pi i j / P), j < P
+    double2 *W = nullptr;     // W[j]  = exp(-2 pi i j / P), j < P   (Bluestein: j < M)
     double2 *CS = nullptr;    // CS[k] = (cos(pi k/P), sin(pi k/P)), k <= P/2
     int *pos = nullptr;       // digit-reversed position of output k
+    int M = 0;                // Bluestein convolution length (0: direct FFT of length P)
+    double2 *chirp = nullptr, *Bhat = nullptr;
 };
 
 struct PassList {
@@ -232,6 +234,7 @@ k_dct_fft(PassList pl, const double2 *__restrict__ W, const double2 *__restrict_
 
 }  // namespace pde
 #include "dct_fft_t.cuh"
+#include "dct_bluestein.cuh"
 namespace pde {
 
 // ---------------------------------------------------------------------------------------
@@ -252,20 +255,127 @@ static bool factor(int P, std::vector<int> &radices)
     return n == 1;
 }
 
+static int bluestein_length(int P)
+{
+    int M = 256;
+    while (M < 2 * P - 1) M <<= 1;
+    return M <= 8192 ? M : 0;
+}
+
 int fft_dct_supported(int L)
 {
     const int P = L - 1;
-    if (P < 2 || (P & 1)) return 0;
+    if (P < 2) return 0;
     std::vector<int> r;
-    if (!factor(P, r)) return 0;
-    if ((size_t)P * 16 > 200 * 1024) return 0;       // one sequence must fit in shared memory
-    return 2;
+    if (!(P & 1) && factor(P, r) && (size_t)P * 16 <= 200 * 1024) return 2;   // direct FFT of length P
+    if (P >= 64 && bluestein_length(P)) return 3;                              // chirp-z on a 2^k FFT
+    return 0;
+}
+
+// digit-reversed position of output k after DIF passes with the given radices
+static int digit_rev(int k, int n, const std::vector<int> &rad)
+{
+    int q = 0;
+    for (int r : rad) {
+        n /= r;
+        q += (k % r) * n;
+        k /= r;
+    }
+    return q;
+}
+
+static int bluestein_create(FftDctPlan **out, int L)
+{
+    const int P = L - 1;
+    const int M = bluestein_length(P);
+    typedef long double ld;
+    const ld pi = 3.141592653589793238462643383279502884L;
+    FftDctPlan *p = new FftDctPlan();
+    p->L = L;
+    p->P = P;
+    p->M = M;
+    std::vector<int> rad;
+    switch (M) {      // must match dispatch_bluestein
+    case 256: rad = {16, 16}; break;
+    case 512: rad = {16, 16, 2}; break;
+    case 1024: rad = {16, 16, 4}; break;
+    case 2048: rad = {16, 16, 8}; break;
+    case 4096: rad = {16, 16, 16}; break;
+    default: rad = {16, 16, 8, 4}; break;
+    }
+    std::vector<double2> W(M), chirp(P), CS((P + 1) / 2 + 1), Bh(M);
+    for (int j = 0; j < M; ++j) {
+        ld ang = 2.0L * pi * (ld)j / (ld)M;
+        W[j] = make_double2((double)cosl(ang), (double)(-sinl(ang)));
+    }
+    std::vector<ld> cr(P), ci(P);
+    for (long long m = 0; m < P; ++m) {
+        const long long q = (m * m) % (2LL * P);          // exact phase index: c_m = exp(i pi q / P)
+        ld ang = pi * (ld)q / (ld)P;
+        cr[m] = cosl(ang);
+        ci[m] = sinl(ang);
+        chirp[m] = make_double2((double)cr[m], (double)ci[m]);
+    }
+    for (int k = 0; k <= (P + 1) / 2; ++k) {
+        ld ang = pi * (ld)k / (ld)P;
+        CS[k] = make_double2((double)cosl(ang), (double)sinl(ang));
+    }
+    // Bhat = FFT_M(wrapped chirp) / M in long double (O(M^2) would be too slow: radix-2 FFT on the host)
+    std::vector<ld> br(M, 0.0L), bi(M, 0.0L);
+    for (int j = 0; j < P; ++j) {
+        br[j] = cr[j];
+        bi[j] = ci[j];
+        if (j) {
+            br[M - j] = cr[j];
+            bi[M - j] = ci[j];
+        }
+    }
+    {   // iterative radix-2 DIT FFT, forward sign
+        int lg = 0;
+        while ((1 << lg) < M) ++lg;
+        for (int i = 0; i < M; ++i) {
+            int j = 0;
+            for (int b = 0; b < lg; ++b)
+                if (i & (1 << b)) j |= 1 << (lg - 1 - b);
+            if (j > i) {
+                std::swap(br[i], br[j]);
+                std::swap(bi[i], bi[j]);
+            }
+        }
+        for (int len = 2; len <= M; len <<= 1) {
+            for (int i = 0; i < M; i += len) {
+                for (int k = 0; k < len / 2; ++k) {
+                    ld ang = -2.0L * pi * (ld)k / (ld)len;
+                    ld wr = cosl(ang), wi = sinl(ang);
+                    ld xr = br[i + k + len / 2] * wr - bi[i + k + len / 2] * wi;
+                    ld xi = br[i + k + len / 2] * wi + bi[i + k + len / 2] * wr;
+                    br[i + k + len / 2] = br[i + k] - xr;
+                    bi[i + k + len / 2] = bi[i + k] - xi;
+                    br[i + k] += xr;
+                    bi[i + k] += xi;
+                }
+            }
+        }
+    }
+    for (int k = 0; k < M; ++k)
+        Bh[digit_rev(k, M, rad)] = make_double2((double)(br[k] / (ld)M), (double)(bi[k] / (ld)M));
+    PDE_CUDA(cudaMalloc(&p->W, sizeof(double2) * M));
+    PDE_CUDA(cudaMalloc(&p->chirp, sizeof(double2) * P));
+    PDE_CUDA(cudaMalloc(&p->CS, sizeof(double2) * CS.size()));
+    PDE_CUDA(cudaMalloc(&p->Bhat, sizeof(double2) * M));
+    PDE_CUDA(cudaMemcpy(p->W, W.data(), sizeof(double2) * M, cudaMemcpyHostToDevice));
+    PDE_CUDA(cudaMemcpy(p->chirp, chirp.data(), sizeof(double2) * P, cudaMemcpyHostToDevice));
+    PDE_CUDA(cudaMemcpy(p->CS, CS.data(), sizeof(double2) * CS.size(), cudaMemcpyHostToDevice));
+    PDE_CUDA(cudaMemcpy(p->Bhat, Bh.data(), sizeof(double2) * M, cudaMemcpyHostToDevice));
+    *out = p;
+    return PDE_OK;
 }
 
 int fft_dct_create(FftDctPlan **out, int L)
 {
     const int P = L - 1;
     std::vector<int> r;
+    if (fft_dct_supported(L) == 3) return bluestein_create(out, L);
     if ((P & 1) || !factor(P, r) || r.size() > 24) {
         set_error("fft_dct_create: L-1 = %d is not an even 2^a 3^b 5^c", P);
         return PDE_ERR_UNSUPPORTED;
@@ -318,6 +428,8 @@ void fft_dct_destroy(FftDctPlan *p)
     cudaFree(p->W);
     cudaFree(p->CS);
     cudaFree(p->pos);
+    cudaFree(p->chirp);
+    cudaFree(p->Bhat);
     delete p;
 }
 
@@ -330,6 +442,16 @@ int fft_dct_exec(FftDctPlan *p, int mode, int njobs, const double *const *xs, lo
         ptrs.y[j] = ys[j];
     }
     const int P = p->P;
+    if (p->M) {
+        BluesteinTables tb{p->W, p->chirp, p->Bhat, p->CS};
+        const int rc = axis == 1 ? dispatch_bluestein<1>(p->M, tb, P, mode, njobs, ptrs, ldx, n_in, ldy, n_out, batch, st)
+                                 : dispatch_bluestein<0>(p->M, tb, P, mode, njobs, ptrs, ldx, n_in, ldy, n_out, batch, st);
+        if (rc < 0) {
+            set_error("pde_dct1: no Bluestein kernel for M = %d", p->M);
+            return PDE_ERR_UNSUPPORTED;
+        }
+        return rc;
+    }
     {   // compile-time specialised kernels for the hot lengths
         const int rc = axis == 1 ? dispatch_fft_t<1>(p, mode, njobs, ptrs, ldx, n_in, ldy, n_out, batch, st)
                                  : dispatch_fft_t<0>(p, mode, njobs, ptrs, ldx, n_in, ldy, n_out, batch, st);

@@ -306,3 +306,42 @@ def test_fft_dct_roundtrip_full_size(dev):
         g = f if axis == 0 else f.T.contiguous()
         back = ops.dct1(plan, ops.BWD, ops.dct1(plan, ops.FWD, g, axis=axis), axis=axis)
         assert float(torch.linalg.norm(back - g) / torch.linalg.norm(g)) < 1e-14
+
+
+@pytest.mark.parametrize("L", [128, 200, 256, 512, 1000, 1024, 2048, 4096])
+@pytest.mark.parametrize("axis", [0, 1])
+def test_bluestein_dct_vs_oracle(dev, L, axis):
+    """Chirp-z DCT-I (algo 3) for lengths whose L-1 is odd / has large prime factors (the Base(N, "CH")
+    sizes with N a power of two: 127 prime, 2047 = 23*89, 4095 = 3^2*5*7*13) against pocketfft."""
+    from pypde_b200 import ops
+    from oracle import pypde_port as P
+    from scipy.fftpack import dctn
+    rng = np.random.default_rng(L + 1)
+    plan = ops.DctPlan(L, algo=3)
+    assert plan.algo == 3
+    nb = 19 if L <= 1024 else 7
+    o = P.Basis(L, "CH")
+    tr = (lambda a: a) if axis == 0 else (lambda a: np.ascontiguousarray(a.T))
+    x = rng.standard_normal((L, nb))
+    tol = 2e-14 * max(1.0, np.log2(L))
+    got = ops.dct1(plan, ops.RAW, T(tr(x), dev), axis=axis)
+    assert rel_l2(tr(H(got)), dctn(x, type=1, axes=(0,))) < tol
+    got = ops.dct1(plan, ops.FWD, T(tr(x), dev), axis=axis)
+    assert rel_l2(tr(H(got)), o.forward(x)) < tol
+    got = ops.dct1(plan, ops.BWD, T(tr(x), dev), axis=axis)
+    assert rel_l2(tr(H(got)), o.backward(x.copy())) < tol
+    n_in, n_out = (2 * L) // 3, (2 * L) // 3 + 1
+    xp = np.zeros((L, nb))
+    xp[:n_in] = x[:n_in]
+    got = ops.dct1(plan, ops.BWD, T(tr(x[:n_in]), dev), axis=axis, n_out=n_out)
+    assert rel_l2(tr(H(got)), o.backward(xp.copy())[:n_out]) < tol
+
+
+def test_auto_algo_selection(dev):
+    from pypde_b200 import ops
+    assert ops.DctPlan(64).algo == 1          # short and odd L-1: dense DMMA matrix
+    assert ops.DctPlan(97).algo == 1          # short: dense wins (1.8 TB/s vs 0.8 TB/s measured)
+    assert ops.DctPlan(769).algo == 2         # L-1 = 768: shared-memory FFT
+    assert ops.DctPlan(3073).algo == 2
+    assert ops.DctPlan(2048).algo == 3        # L-1 = 2047 = 23 * 89: Bluestein
+    assert ops.DctPlan(6144).algo == 1        # L-1 = 6143 prime, M = 16384 does not fit: dense fallback
