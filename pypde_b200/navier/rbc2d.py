@@ -239,10 +239,14 @@ class NavierStokes(NavierStokesBase, Integrator):
 
     def _update_graph(self):
         fs = self._fast
-        cur = tuple(t.data_ptr() for t in (self.T.vhat, self.U.vhat, self.V.vhat, self.P.vhat, self.pres.vhat))
-        if self._graph is None or cur != fs.bound:
+        if self._slab:
+            stale = not fs.bound
+        else:
+            cur = tuple(t.data_ptr() for t in (self.T.vhat, self.U.vhat, self.V.vhat, self.P.vhat, self.pres.vhat))
+            stale = cur != fs.bound
+        if self._graph is None or stale:
             fs.bind()
-            for rk in range(self.nstage):      # warm-up outside the capture (plan tables, attributes)
+            for rk in range(self.nstage):      # warm-up outside the capture (plan tables, attributes, NCCL)
                 fs.stage_calls[rk].run()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
