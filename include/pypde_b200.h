@@ -229,6 +229,15 @@ int pde_conv_products(long n, double b, double c, const double *u, const double 
 int pde_dct1_multi(pde_dct_plan_t plan, int mode, int njobs, const double *const *x, long ldx, int n_in,
                    double *const *y, long ldy, int n_out, int batch, int axis, void *stream);
 
+/* ---- slab decomposition: pack / unpack of a bundle for the all-to-all transposes -------
+ * bundle : (rows, K*cols) row-major, K arrays side by side (array k = columns k*cols .. k*cols+cols-1)
+ * blocked: for every rank s (columns col_off[s] .. col_off[s+1]-1) a contiguous block (rows, K, w_s)
+ * dir = 1: bundle -> blocked (pack before sending in the Y -> X transpose),
+ * dir = 0: blocked -> bundle (unpack after receiving in the X -> Y transpose).
+ * col_off is a HOST array of nranks+1 offsets (nranks <= 16). */
+int pde_slab_repack(int dir, double *bundle, double *blocked, int rows, int K, int cols, int nranks,
+                    const int *col_off, void *stream);
+
 /* ---- layout helper ------------------------------------------------------------- */
 /* out(n1 x n0) = in(n0 x n1)^T */
 int pde_transpose(const double *in, long ldin, double *out, long ldout, int n0, int n1, void *stream);

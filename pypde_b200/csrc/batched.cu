@@ -100,6 +100,35 @@ __global__ void k_conv_products(long n, double b, double c, const double *__rest
     }
 }
 
+struct SlabOff {
+    int n;
+    int off[17];
+};
+
+__global__ void k_slab_repack(int dir, double *__restrict__ bundle, double *__restrict__ blocked, int rows, int K,
+                              int cols, SlabOff so)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.z;
+    if (j >= cols) return;
+    int s = 0;
+    while (s + 1 < so.n && j >= so.off[s + 1]) ++s;
+    const int w = so.off[s + 1] - so.off[s];
+    const long bbase = (long)rows * K * so.off[s] + (long)k * w + (j - so.off[s]);
+    const long gbase = (long)k * cols + j;
+    const long bstep = (long)K * w, gstep = (long)K * cols;
+    // 8 rows per thread: independent 8-byte transfers in flight, index math amortised
+    const int i0 = blockIdx.y * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int i = i0 + e;
+        if (i < rows) {
+            if (dir) blocked[bbase + i * bstep] = bundle[gbase + i * gstep];
+            else bundle[gbase + i * gstep] = blocked[bbase + i * bstep];
+        }
+    }
+}
+
 }  // namespace pde
 
 using namespace pde;
@@ -195,6 +224,20 @@ int pde_lincomb_multi(int njobs, const pde_lincomb_job *jobs, void *stream)
     dim3 block(64, 4), grid(ceil_div(m1, 64), ceil_div(m0, 4), njobs);
     k_lincomb_multi<<<grid, block, 0, as_stream(stream)>>>(lj);
     return after_launch("pde_lincomb_multi");
+}
+
+int pde_slab_repack(int dir, double *bundle, double *blocked, int rows, int K, int cols, int nranks,
+                    const int *col_off, void *stream)
+{
+    PDE_REQUIRE(bundle && blocked && col_off, "null pointer");
+    PDE_REQUIRE(nranks >= 1 && nranks <= 16, "1..16 ranks");
+    if (rows <= 0 || K <= 0 || cols <= 0) return PDE_OK;
+    SlabOff so{};
+    so.n = nranks;
+    for (int s = 0; s <= nranks; ++s) so.off[s] = col_off[s];
+    dim3 block(256), grid(ceil_div(cols, 256), ceil_div(rows, 8), K);
+    k_slab_repack<<<grid, block, 0, as_stream(stream)>>>(dir, bundle, blocked, rows, K, cols, so);
+    return after_launch("pde_slab_repack");
 }
 
 int pde_conv_products(long n, double b, double c, const double *u, const double *w, const double *u_old,

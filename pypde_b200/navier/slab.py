@@ -18,6 +18,8 @@ All spectral arrays are padded to the common kind (N0, N1) (Galerkin arrays have
 rows / columns), dealiased ones to (D0, N1), so one row partition (of N0, D0) and one column
 partition (of N1) serve every exchange.  10 exchanges per IMEX stage.
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
 
@@ -43,6 +45,27 @@ class SlabComm:
         self.bytes_sent = 0
         self.calls = 0
 
+    def _repack(self, direction, bundle, blocked, rows, K, cols, cp):
+        """One kernel (pde_slab_repack) on CUDA tensors; per-rank torch copies otherwise (gloo tests)."""
+        if bundle.is_cuda:
+            from .. import _cabi as C
+            off = (ctypes.c_int * (self.size + 1))(*([o for o, _ in cp] + [cols]))
+            C.check(C.lib().pde_slab_repack(direction, C.p(bundle), C.p(blocked), rows, K, cols, self.size, off,
+                                            C.stream()))
+            return
+        b3 = bundle.view(rows, K, cols)
+        pos = 0
+        for s in range(self.size):
+            o, w = cp[s]
+            n = rows * K * w
+            if n:
+                blk = blocked[pos:pos + n].view(rows, K, w)
+                if direction:
+                    blk.copy_(b3[:, :, o:o + w])
+                else:
+                    b3[:, :, o:o + w].copy_(blk)
+            pos += n
+
     def x2y(self, xb, yb, K, rows, cols):
         """xb: (rows, K*cols_r) X bundle of this rank; yb: (rows_r, K*cols) Y bundle (output)."""
         P, r = self.size, self.rank
@@ -55,13 +78,7 @@ class SlabComm:
         dist.all_to_all_single(recv, xb.reshape(-1), out_split, in_split, group=self.group)
         self.bytes_sent += (sum(in_split) - in_split[r]) * 8
         self.calls += 1
-        y3 = yb.view(rp[r][1], K, cols)
-        off = 0
-        for s in range(P):
-            w = cp[s][1]
-            if w and rp[r][1]:
-                y3[:, :, cp[s][0]:cp[s][0] + w].copy_(recv[off:off + out_split[s]].view(rp[r][1], K, w))
-            off += out_split[s]
+        self._repack(0, yb, recv, rp[r][1], K, cols, cp)
         return yb
 
     def y2x(self, yb, xb, K, rows, cols):
@@ -73,13 +90,7 @@ class SlabComm:
         in_split = [rp[r][1] * K * cp[s][1] for s in range(P)]
         out_split = [rp[s][1] * K * cp[r][1] for s in range(P)]
         send = torch.empty(sum(in_split), dtype=yb.dtype, device=yb.device)
-        y3 = yb.view(rp[r][1], K, cols)
-        off = 0
-        for s in range(P):
-            w = cp[s][1]
-            if w and rp[r][1]:
-                send[off:off + in_split[s]].view(rp[r][1], K, w).copy_(y3[:, :, cp[s][0]:cp[s][0] + w])
-            off += in_split[s]
+        self._repack(1, yb, send, rp[r][1], K, cols, cp)
         dist.all_to_all_single(xb.reshape(-1), send, out_split, in_split, group=self.group)
         self.bytes_sent += (sum(in_split) - in_split[r]) * 8
         self.calls += 1
