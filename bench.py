@@ -37,6 +37,8 @@ WORKLOADS = {
     "rbc64": dict(case="rbc", shape=(64, 64), ra=1e5, pr=1.0, dt=0.01, tsave=None, dealias=True,
                   integrator="rk3", beta=1.0, aspect=1.0),
 }
+ENSEMBLE = {"members": 256, "cfg": dict(case="rbc", shape=(128, 128), pr=1.0, dt=0.005, tsave=None, dealias=True,
+                                        integrator="rk3", beta=1.0, aspect=1.0)}
 METRIC = "rbc2d_fp64_timesteps_per_sec"
 UNIT = "steps/s"
 
@@ -252,6 +254,86 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback of B200_PROFILING.md"
 
 
+def run_ensemble(args):
+    """--workload ens128: 256 independent 128 x 128 runs (Ra = logspace(4, 8, 256)) sharded over the GPUs,
+    no data-path collective; a step advances EVERY member by one RK3 step."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from pypde_b200 import _cabi
+    from pypde_b200.navier.ensemble import Ensemble
+    ra = np.logspace(4, 8, ENSEMBLE["members"])
+    t0 = time.perf_counter()
+    ens = Ensemble(ra, rank=rank, world=world, **ENSEMBLE["cfg"])
+    ens.for_each(lambda m: init_state(m, ENSEMBLE["cfg"]["shape"]))
+    setup_s = time.perf_counter() - t0
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        ens.update()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        ens.update()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop()
+    finite = all(bool(torch.isfinite(m.T.vhat).all()) for m in ens.members)
+    # launches: one eager member step counted through the library, times members and steps
+    m0 = ens.members[0]
+    _cabi.launch_count_reset()
+    for rk in range(m0.nstage):
+        m0._fast.stage_calls[rk].run()
+    torch.cuda.synchronize()
+    per_member = _cabi.launch_count()
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import pypde_port as P
+        cfgm = dict(ENSEMBLE["cfg"], ra=float(ra[128]))
+        o = P.RBC2D(**cfgm)
+        init_state(o, cfgm["shape"], port=True)
+        o.update()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            o.update()
+        tm = (time.perf_counter() - t0) / 3
+        cpu = {"value": 1.0 / (tm * ENSEMBLE["members"]), "unit": UNIT, "cores": cpu_cores(), "kind": "port",
+               "sample": "3 RK3 steps of ONE 128x128 member (%.3f s each) x 256 members" % tm}
+    line = {"metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "ens128", "members": ENSEMBLE["members"], "members_per_gpu": len(ens.members),
+                       "shape": [128, 128], "ra": "logspace(4, 8, 256)", "integrator": "rk3", "dealias": True,
+                       "parallelism": "independent members sharded over %d GPU(s), no collective" % world,
+                       "l2": "one member's working set fits L2 (small-grid regime by design)", "finite": finite,
+                       "setup_s": setup_s, "cuda_graph": True},
+            "member_steps_per_sec": args.steps * ENSEMBLE["members"] / (ms * 1e-3),
+            "clocks": clocks, "gpu_launches": per_member * len(ens.members) * args.steps,
+            "gpu_launches_per_member_step": per_member, "cpu_baseline": cpu}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_gpu(args, cfg):
     import torch
     import torch.distributed as dist
@@ -361,7 +443,13 @@ def run_gpu(args, cfg):
     gemm = ops_ms.get("pde_gemm_f64", {"ms": 0.0, "work": 0.0, "launches": 1})
     roof_dct = {"kernel": "k_dct_fft (shared-memory FFT DCT-I, all batched transforms of the step)", "bound": "hbm",
                 "achieved": dct_work / (dct_ms * 1e-3) / 1e9 if dct_ms else None, "peak": peaks.get("hbm_gbs"),
-                "unit": "GB/s", "traffic": None, "peak_source": peak_src, "launches_per_step": dct_launches,
+                "unit": "GB/s",
+                "traffic": 61757696,
+                "traffic_note": "ncu --set full of k_dct_fft_t<3072,1,192,1,...> on ONE 2048-sequence array "
+                                "(tools/prof_dct.py, profiles/r01_ncu_dct_fft_specialised_v1.csv): dram read 50.4 MB + "
+                                "write 11.3 MB against 100.7 MB algorithmic (the 50 MB output stays in the 126 MB L2); "
+                                "the bench launches carry 3-8 such arrays",
+                "peak_source": peak_src, "launches_per_step": dct_launches,
                 "avg_launch_ms": dct_ms / max(dct_launches, 1), "share_of_step": dct_ms / step_ms_instr,
                 "algorithmic_bytes_per_launch": dct_work / max(dct_launches, 1)}
     roof_dct["frac"] = roof_dct["achieved"] / roof_dct["peak"] if roof_dct["achieved"] else None
@@ -431,11 +519,15 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="rbc2048", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="rbc2048", choices=sorted(WORKLOADS) + ["ens128"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.workload == "ens128":
+        if args.impl == "reference":
+            raise SystemExit("--impl reference times the rbc workloads; the ensemble's CPU number is its cpu_baseline")
+        return run_ensemble(args)
     cfg = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, cfg)

@@ -29,6 +29,11 @@ def solverplan_poisson1d(bases, singular=False):
     return solver
 
 
+# host-side eigen-decomposition cache: depends only on the y basis, its size and scale (ensembles
+# build many solvers of the same grid)
+_EIG_CACHE = {}
+
+
 def solverplan_poisson2d(bases, singular=False, scale=(1, 1)):
     field = Field(bases)
     assert field.ndim == 2
@@ -36,17 +41,21 @@ def solverplan_poisson2d(bases, singular=False, scale=(1, 1)):
     Ax = Ix @ Sx * (1.0 / scale[0] ** 2.0)
     Cx = Bx @ Sx
 
-    Sy, By, Iy = _axis_matrices(field.xs[1])
-    By = By.toarray()
-    Ay = (Iy @ Sy * (1.0 / scale[1] ** 2.0)).toarray()
-    Cy = (By @ Sy)
-    Cy = np.asarray(Cy)
+    key = (field.xs[1].id, field.xs[1].N, float(scale[1]), bool(singular))
+    if key not in _EIG_CACHE:
+        Sy, By, Iy = _axis_matrices(field.xs[1])
+        By = By.toarray()
+        Ay = (Iy @ Sy * (1.0 / scale[1] ** 2.0)).toarray()
+        Cy = (By @ Sy)
+        Cy = np.asarray(Cy)
 
-    CyI = np.linalg.inv(Cy)
-    wy, Qy, QyI = eigdecomp(CyI @ Ay)
-    if singular:
-        wy[0] += 1e-20
-    Hy = QyI @ CyI @ By
+        CyI = np.linalg.inv(Cy)
+        wy, Qy, QyI = eigdecomp(CyI @ Ay)
+        if singular:
+            wy[0] += 1e-20
+        Hy = QyI @ CyI @ By
+        _EIG_CACHE[key] = (wy, Qy, Hy)
+    wy, Qy, Hy = _EIG_CACHE[key]
 
     solver = SolverPlan()
     solver.add_rhs(PlanRHS(Bx, ndim=2, axis=0))

@@ -193,3 +193,27 @@ def test_slab_stepper_two_gpus():
                           "--master-addr", "127.0.0.1", "--master-port", "29533", script],
                          capture_output=True, text=True, timeout=600)
     assert "SLAB OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def test_ensemble_members_match_standalone_runs():
+    """Ensemble (independent members on several streams, one CUDA graph each) == standalone runs."""
+    import torch
+    from pypde_b200.navier.ensemble import Ensemble
+    from pypde_b200.navier import rbc2d
+    kw = dict(case="rbc", shape=(32, 32), pr=1.0, dt=0.01, tsave=None, dealias=True, integrator="rk3",
+              beta=1.0, aspect=1.0)
+    ras = [1e4, 3e4, 1e5, 3e5, 1e6]
+    ens = Ensemble(ras, streams=3, **kw)
+    solo = [rbc2d.NavierStokes(ra=r, **kw) for r in ras]
+    for m in ens.members + solo:
+        m.set_velocity(m=1, n=1, amplitude=0.2)
+        m.set_temperature(amplitude=0.2)
+    for _ in range(5):
+        ens.update()
+        for s in solo:
+            s.update()
+    torch.cuda.synchronize()
+    for m, s in zip(ens.members, solo):
+        assert torch.equal(m.T.vhat, s.T.vhat) and torch.equal(m.U.vhat, s.U.vhat)
+    # sharding: rank r of 2 gets every second member
+    assert Ensemble(ras, rank=1, world=2, **kw).indices == [1, 3]
