@@ -2,7 +2,7 @@
 """
 bench.py - headline benchmark of pypde_b200 (contract: see README / DESIGN.md §measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload rbc2048|rbc512|rbc64]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload rbc2048|rbc512|rbc64|ens128|diff1024]
     python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
 
 Metric (BASELINE.json): RBC2D fp64 timesteps/sec at N x N.  A "step" is one full IMEX RK3 time
@@ -513,13 +513,112 @@ def run_gpu(args, cfg):
         dist.destroy_process_group()
 
 
+def run_diffusion(args):
+    """--workload diff1024 (BASELINE.json configs[2]): theta-scheme steps of the 2-D diffusion example
+    with a Dirichlet wall at 1024 x 1024 through the generic Field / grad / SolverPlan API (no fused
+    stepper: this is the plan-by-plan path a user script takes).  Single GPU."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "diffusion"))
+    from diff_2d_bc import Diffusion2d
+    from pypde_b200 import _cabi
+    torch.cuda.set_device(0)
+    cfg = dict(shape=(1024, 1024), dt=0.01, kappa=0.1, beta=0.5)
+    D = Diffusion2d(tsave=None, **cfg)
+    for _ in range(args.warmup):
+        D.update()
+    torch.cuda.synchronize()
+    _cabi.launch_count_reset()
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        D.update()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = _cabi.launch_count()
+    clocks = sampler.stop()
+    # end to end: the coefficient array comes from / returns to pinned host memory every step
+    hin = D.field.vhat.cpu().pin_memory()
+    hout = torch.empty_like(hin).pin_memory()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        D.field.vhat.copy_(hin, non_blocking=True)
+        D.update()
+        hout.copy_(D.field.vhat, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        hin, hout = hout, hin
+    e1.record()
+    torch.cuda.synchronize()
+    ms_e2e = e0.elapsed_time(e1)
+    nb = hin.numel() * 8
+    finite = bool(torch.isfinite(D.field.vhat).all())
+    # the same step replayed from a CUDA graph (removes the Python / launch overhead of the generic path)
+    static = D.field.vhat
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        D.update()
+        static.copy_(D.field.vhat)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        D.update()
+        static.copy_(D.field.vhat)
+    D.field.vhat = static
+    for _ in range(args.warmup):
+        graph.replay()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        graph.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_graph = e0.elapsed_time(e1)
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import pypde_port as P
+        o = P.Diffusion2D(**cfg)
+        o.update()
+        t0 = time.perf_counter()
+        for _ in range(20):
+            o.update()
+        tm = (time.perf_counter() - t0) / 20
+        cpu = {"value": 1.0 / tm, "unit": UNIT, "cores": cpu_cores(), "kind": "port",
+               "sample": "20 steps of the oracle Diffusion2D at 1024x1024 (%.3f s each)" % tm}
+    # algorithmic traffic of one step: 2 mixed second derivatives (stencil + two recurrences each: 3 passes),
+    # 2 axpy, solve_rhs (2 banded products), solve_old (2), 1 add, solve_lhs (2 sweeps): 16 passes, read + write
+    N = 1024
+    bytes_step = 16 * 2 * 8 * N * N
+    peaks, peak_src = measured_peaks()
+    achieved = bytes_step * args.steps / (ms * 1e-3) / 1e9
+    line = {"metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "diff1024", "shape": [N, N], "bases": ["CD", "CN"], "dt": 0.01, "kappa": 0.1,
+                       "beta": 0.5, "path": "generic plan-by-plan API (grad, SolverPlan), eager launches",
+                       "l2": "arrays are 8 MB each: the step's working set fits the 126 MB L2 (by the size of the "
+                             "config)", "finite": finite},
+            "clocks": clocks,
+            "e2e": {"value": args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": nb,
+                    "d2h_bytes_per_step": nb},
+            "gpu_launches": launches, "graph_ms_per_step": ms_graph / args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                         "note": "whole step, 16 axis passes x (read + write) x 8 B x N^2 = %d B" % bytes_step},
+            "cpu_baseline": cpu}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="rbc2048", choices=sorted(WORKLOADS) + ["ens128"])
+    ap.add_argument("--workload", default="rbc2048", choices=sorted(WORKLOADS) + ["ens128", "diff1024"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
@@ -528,6 +627,10 @@ def main():
         if args.impl == "reference":
             raise SystemExit("--impl reference times the rbc workloads; the ensemble's CPU number is its cpu_baseline")
         return run_ensemble(args)
+    if args.workload == "diff1024":
+        if args.impl == "reference":
+            raise SystemExit("--impl reference times the rbc workloads; diff1024's CPU number is its cpu_baseline")
+        return run_diffusion(args)
     cfg = WORKLOADS[args.workload]
     if args.impl == "reference":
         run_reference(args, cfg)

@@ -406,6 +406,41 @@ class Poisson1D:
 # -----------------------------------------------------------------------------
 # Rayleigh-Benard stepper (navier/rbc2d.py + navier/rbc2d_base.py)
 # -----------------------------------------------------------------------------
+class Diffusion2D:
+    """The reference's 2-D diffusion example with an inhomogeneous Dirichlet wall
+    (diffusion/diff_2d-bc.py:9-105): du/dt = kappa lap(u), bases (CD, CN), u(x=-1, y) = cos(pi y),
+    theta-scheme with the ADI Helmholtz template (templates/hholtz.py:42-93)."""
+
+    def __init__(self, shape=(20, 20), bases=("CD", "CN"), kappa=1.0, dt=0.2, beta=0.5):
+        self.shape, self.kappa, self.dt, self.beta = tuple(shape), kappa, dt, beta
+        self.space = Space([Basis(shape[0], bases[0]), Basis(shape[1], bases[1])])
+        self.vhat = np.zeros(self.space.shape_spectral)
+        self.time = 0.0
+        # diff_2d-bc.py:79-85
+        bc = np.zeros((2, shape[1]))
+        bc[0, :] = np.cos(np.pi * self.space.y)
+        self.sbc, self.bc_v, self.bc_vhat = field_bc(self.space.xs, 0, bc)
+        # diff_2d-bc.py:74-77
+        self.solver = HelmholtzADI(self.space.xs, lam=dt * kappa * beta)
+        # diff_2d-bc.py:87-92
+        self.fhat = dt * kappa * self.sbc.grad(self.bc_vhat, (0, 2))
+
+    def update(self):
+        """diff_2d-bc.py:94-105"""
+        c = self.dt * self.kappa * (1.0 - self.beta)
+        rhs = self.fhat.copy()
+        rhs += c * self.space.grad(self.vhat, (0, 2))
+        rhs += c * self.space.grad(self.vhat, (2, 0))
+        rhs = self.solver.solve_rhs(rhs)
+        rhs += self.solver.solve_old(self.vhat)
+        self.vhat = self.solver.solve_lhs(rhs)
+        self.time += self.dt
+
+    def total(self):
+        """Physical field including the lifting (diff_2d-bc.py:134-135)."""
+        return self.space.backward(self.vhat) + self.bc_v
+
+
 def transfer_function(TL, TM, TR, x, k=0.01):
     """navier/rbc2d.py:437-446"""
     arr = np.zeros(x.shape)

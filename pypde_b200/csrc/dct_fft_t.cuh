@@ -179,7 +179,7 @@ k_dct_fft_t(const double2 *__restrict__ W, const double2 *__restrict__ CS, int m
     if (ns == S) {
         // full CTA: compile-time trip count, all global loads of a batch issued before the first use
         constexpr int ITER = (S * P + T - 1) / T;
-        constexpr int UB = 8;                                   // loads in flight per thread: 2 * UB
+        constexpr int UB = AXIS == 1 ? 16 : 8;                  // loads in flight per thread: 2 * UB (16 thrashes on axis 0)
 #pragma unroll 1
         for (int it0 = 0; it0 < ITER; it0 += UB) {
             double v0[UB], v1[UB];

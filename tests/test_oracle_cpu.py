@@ -140,3 +140,21 @@ def _cases():
         "rbc128_rk3_dealias": dict(case="rbc", shape=(128, 128), ra=1e6, pr=1.0, dt=0.005, tsave=None, dealias=True,
                                    integrator="rk3", beta=1.0, aspect=1.0),
     }
+
+
+@pytest.mark.parametrize("name,cfg,snaps", [
+    ("d48x40", dict(shape=(48, 40), dt=0.01, kappa=0.1, beta=0.5), (1, 10, 100)),
+    ("d33x64_beta1", dict(shape=(33, 64), dt=0.02, kappa=0.05, beta=1.0), (1, 20))])
+def test_diffusion_port_matches_reference(name, cfg, snaps):
+    """oracle Diffusion2D against the states of the unmodified reference script
+    diffusion/diff_2d-bc.py (tests/golden/make_golden_diffusion.py)."""
+    g = load_golden("diffusion")
+    o = P.Diffusion2D(**cfg)
+    assert rel_l2(o.fhat, g[name + "_fhat"]) < 1e-13
+    step = 0
+    for s in snaps:
+        while step < s:
+            o.update()
+            step += 1
+        assert rel_l2(o.vhat, g["%s_vhat_%d" % (name, s)]) < 1e-12, s
+    assert rel_l2(o.total(), g[name + "_total"]) < 1e-12
