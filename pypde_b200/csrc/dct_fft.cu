@@ -29,6 +29,7 @@ struct FftDctPlan {
     int npass = 0;
     int radix[24];
     double2 *W = nullptr;     // W[j]  = exp(-2 pi i j / P), j < P   (Bluestein: j < M)
+    double2 *Wp = nullptr;    // per-pass [r][j] twiddle tables of the specialised kernels (built on first use)
     double2 *CS = nullptr;    // CS[k] = (cos(pi k/P), sin(pi k/P)), k <= P/2
     int *pos = nullptr;       // digit-reversed position of output k
     int M = 0;                // Bluestein convolution length (0: direct FFT of length P)
@@ -426,6 +427,7 @@ void fft_dct_destroy(FftDctPlan *p)
 {
     if (!p) return;
     cudaFree(p->W);
+    cudaFree(p->Wp);
     cudaFree(p->CS);
     cudaFree(p->pos);
     cudaFree(p->chirp);

@@ -9,8 +9,19 @@
 // shared-memory round trips instead of six) and the digit reversal is arithmetic.
 // Same algorithm and data flow as k_dct_fft (see dct_fft.cu).
 #pragma once
+#include <type_traits>
 
 namespace pde {
+
+// compile-time loop: f(std::integral_constant<int, I>) for I in [I0, N)
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
 
 template <>
 __device__ __forceinline__ void dft<8>(double2 *a)
@@ -81,7 +92,12 @@ struct Pad {
     __device__ __forceinline__ static int phys(int i) { return i + i / M1; }
 };
 
-template <int P, int M1, int NCUR, int S, int T, int R>
+// Twiddles of a DIF pass.  WOFF < 0: the plain table W[t] = exp(-2 pi i t / P), read with stride (Bluestein
+// kernels).  WOFF >= 0: per-pass tables laid out [r][j] (entry (r - 1) * M + j = W_NCUR^{j r}) starting at
+// W + WOFF: consecutive lanes (consecutive j) read consecutive entries.  ncu on the strided version showed the
+// L1TEX pipe 77 % busy -- a warp's request for W[j * r] touches up to 60 cache lines in the first pass, as
+// many L1 cycles as all shared-memory traffic of the pass; same values, so results are bit-identical.
+template <int WOFF, int P, int M1, int NCUR, int S, int T, int R>
 __device__ __forceinline__ void dif_pass_t(double2 *z, const double2 *__restrict__ W)
 {
     constexpr int M = NCUR / R, PER_SEQ = P / R, TOTAL = S * PER_SEQ, TWS = P / NCUR;
@@ -103,22 +119,43 @@ __device__ __forceinline__ void dif_pass_t(double2 *z, const double2 *__restrict
         dft<R>(a);
         if (M > 1) {
 #pragma unroll
-            for (int r = 1; r < R; ++r) a[r] = cmul(a[r], __ldg(W + j * (r * TWS)));
+            for (int r = 1; r < R; ++r)
+                a[r] = cmul(a[r], WOFF < 0 ? __ldg(W + j * (r * TWS)) : __ldg(W + WOFF + (r - 1) * M + j));
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) p[r * RS] = a[r];
     }
 }
 
-template <int P, int M1, int NCUR, int S, int T, int R, int... Rest>
-struct DifPasses {
+template <int WOFF, int P, int M1, int NCUR, int S, int T, int R, int... Rest>
+struct DifPassesW {
     __device__ __forceinline__ static void run(double2 *z, const double2 *__restrict__ W)
     {
-        dif_pass_t<P, M1, NCUR, S, T, R>(z, W);
+        dif_pass_t<WOFF, P, M1, NCUR, S, T, R>(z, W);
         __syncthreads();
-        if constexpr (sizeof...(Rest) > 0) DifPasses<P, M1, NCUR / R, S, T, Rest...>::run(z, W);
+        constexpr int NEXT = WOFF < 0 ? -1 : WOFF + (NCUR / R > 1 ? (R - 1) * (NCUR / R) : 0);
+        if constexpr (sizeof...(Rest) > 0) DifPassesW<NEXT, P, M1, NCUR / R, S, T, Rest...>::run(z, W);
     }
 };
+
+template <int P, int M1, int NCUR, int S, int T, int... RAD>
+struct DifPasses : DifPassesW<-1, P, M1, NCUR, S, T, RAD...> {
+};
+
+// host: the [r][j] tables of all passes, concatenated in pass order (offsets as in DifPassesW)
+template <int R, int... Rest>
+static void build_pass_tables(int P, int ncur, std::vector<double2> &out)
+{
+    const long double pi = 3.141592653589793238462643383279502884L;
+    const int M = ncur / R, tws = P / ncur;
+    if (M > 1)
+        for (int r = 1; r < R; ++r)
+            for (int j = 0; j < M; ++j) {
+                const long double ang = 2.0L * pi * (long double)((long)j * r * tws) / (long double)P;
+                out.push_back(make_double2((double)cosl(ang), (double)(-sinl(ang))));
+            }
+    if constexpr (sizeof...(Rest) > 0) build_pass_tables<Rest...>(P, M, out);
+}
 
 template <int R, int... Rest>
 struct FirstRadix {
@@ -136,8 +173,26 @@ struct DigitRev {
     }
 };
 
+// Register cap: what the CTAs that fit an SM by shared memory (at most 3) can share.  Registers are granted
+// per warp in coarse units (ncu: a 106-register kernel = 3392 per warp was limited to TWO 6-warp CTAs, i.e. it
+// was charged 4096), so the cap is rounded down to a multiple of 32 per thread: 96 is what lets three
+// 192-thread CTAs run together.  Never below 96 (the radix-16 butterfly needs ~100): fewer CTAs instead.
+constexpr int fft_regs(int ctas, int T)
+{
+    const int per_thread = 65536 / (ctas * (T / 32)) / 1024 * 1024 / 32;
+    return per_thread > 168 ? 168 : per_thread;
+}
+template <int P, int S, int T, int R1>
+struct FftRegs {
+    static constexpr int SMEM = S * Pad<P, P / R1>::SEQ * 16 + 1024;
+    static constexpr int FIT = 227 * 1024 / SMEM;
+    static constexpr int C3 = FIT < 1 ? 1 : (FIT > 3 ? 3 : FIT);
+    static constexpr int CTAS = fft_regs(C3, T) >= 96 ? C3 : (C3 > 1 && fft_regs(C3 - 1, T) >= 96 ? C3 - 1 : 1);
+    static constexpr int value = fft_regs(CTAS, T);
+};
+
 template <int P, int S, int T, int AXIS, int... RAD>
-__global__ void __launch_bounds__(T)
+__global__ void __maxnreg__((FftRegs<P, S, T, FirstRadix<RAD...>::value>::value))
 k_dct_fft_t(const double2 *__restrict__ W, const double2 *__restrict__ CS, int mode, DctPtrs ptrs, long ldx,
             int n_in, long ldy, int n_out, int batch)
 {
@@ -177,23 +232,56 @@ k_dct_fft_t(const double2 *__restrict__ W, const double2 *__restrict__ CS, int m
         dst = s * PS + PD::phys(m);
     };
     if (ns == S) {
-        // full CTA: compile-time trip count, all global loads of a batch issued before the first use
-        constexpr int ITER = (S * P + T - 1) / T;
-        constexpr int UB = AXIS == 1 ? 16 : 8;                  // loads in flight per thread: 2 * UB (16 thrashes on axis 0)
-#pragma unroll 1
-        for (int it0 = 0; it0 < ITER; it0 += UB) {
+        // Full CTA.  The iteration index is a compile-time constant and the thread index enters through
+        // per-thread invariants, so the (sequence, element) split costs nothing per element (the generic
+        // form below spent 44 instructions per element, 29 % of the kernel's instruction stream, on index
+        // arithmetic).  Loads are issued in batches of UB iterations before their first use.
+        static_assert((S * P) % T == 0, "S * P must be a multiple of T");
+        constexpr int ITER = S * P / T;
+        constexpr int UB = ITER < 16 ? ITER : (AXIS == 1 ? 16 : 8);
+        static_assert(ITER % UB == 0, "load batches");
+        static_assert(AXIS == 1 ? (P % T == 0 || T % P == 0) : (T % S == 0 && P % (T / S) == 0), "thread mapping");
+        constexpr int C = AXIS == 1 ? (P % T == 0 ? T : P) : T / S;     // elements of one sequence per iteration
+        constexpr int SPI = AXIS == 1 ? (P % T == 0 ? 0 : T / P) : 0;   // axis 1, short sequences: sequences per iteration
+        const int ld32 = (int)ldx;
+        // per-thread invariants
+        const int tm = AXIS == 1 ? (int)threadIdx.x % C : (int)threadIdx.x / S;      // element offset within the iteration
+        const int ts = AXIS == 1 ? (int)threadIdx.x / C : (int)threadIdx.x % S;      // sequence offset
+        const double *tsrc = AXIS == 1 ? x + (long)(q0 + ts) * ld32 : x + q0 + ts;
+        double2 *tz = zsm + ts * PS;
+        static_for<0, ITER / UB>([&](auto bc) {
+            constexpr int B0 = decltype(bc)::value * UB;
             double v0[UB], v1[UB];
-            int dst[UB];
-#pragma unroll
-            for (int u = 0; u < UB; ++u) {
-                const int idx = (it0 + u) * T + threadIdx.x;
-                dst[u] = -1;
-                if (it0 + u < ITER && idx < S * P) load_one(idx, S, v0[u], v1[u], dst[u]);
-            }
-#pragma unroll
-            for (int u = 0; u < UB; ++u)
-                if (dst[u] >= 0) zsm[dst[u]] = make_double2(v0[u], v1[u]);
-        }
+            static_for<0, UB>([&](auto uc) {
+                constexpr int u = decltype(uc)::value, it = B0 + u;
+                // axis 1, P % T == 0: sequence it / (P / T), element (it % (P / T)) * T + tm
+                // axis 1, T % P == 0: sequence it * SPI + ts,  element tm
+                // axis 0:             sequence ts,             element it * C + tm
+                constexpr int sc = AXIS == 1 ? (P % T == 0 ? it / (P / T) : it * SPI) : 0;
+                constexpr int mc = AXIS == 1 ? (P % T == 0 ? (it % (P / T)) * T : 0) : it * C;
+                const int m = mc + tm;
+                const bool lo = (mc + C <= H) ? true : (mc >= H ? false : m < H);
+                const int n0 = lo ? 2 * m : 2 * P - 2 * m;
+                const int n1 = lo ? n0 + 1 : n0 - 1;
+                const double *src = AXIS == 1 ? tsrc + (long)sc * ld32 : tsrc;
+                if (AXIS == 1) {
+                    v0[u] = n0 < n_in ? __ldg(src + n0) : 0.0;
+                    v1[u] = n1 < n_in ? __ldg(src + n1) : 0.0;
+                } else {
+                    v0[u] = n0 < n_in ? __ldg(src + (long)n0 * ld32) : 0.0;
+                    v1[u] = n1 < n_in ? __ldg(src + (long)n1 * ld32) : 0.0;
+                }
+            });
+            static_for<0, UB>([&](auto uc) {
+                constexpr int u = decltype(uc)::value, it = B0 + u;
+                constexpr int sc = AXIS == 1 ? (P % T == 0 ? it / (P / T) : it * SPI) : 0;
+                constexpr int mc = AXIS == 1 ? (P % T == 0 ? (it % (P / T)) * T : 0) : it * C;
+                const int m = mc + tm;
+                // the end points x_0 (m = 0, even slot) and x_P (m = H, even slot) are not scaled
+                const bool edge = (mc == 0 && tm == 0) || (mc <= H && H < mc + C && m == H);
+                tz[sc * PS + PD::phys(m)] = make_double2(v0[u] * (edge ? 1.0 : se), v1[u] * so);
+            });
+        });
     } else {
         for (int idx = threadIdx.x; idx < ns * P; idx += T) {
             double v0, v1;
@@ -203,38 +291,66 @@ k_dct_fft_t(const double2 *__restrict__ W, const double2 *__restrict__ CS, int m
         }
     }
     __syncthreads();
-    DifPasses<P, M1, P, S, T, RAD...>::run(zsm, W);
+    DifPassesW<0, P, M1, P, S, T, RAD...>::run(zsm, W);          // W: per-pass [r][j] tables (p->Wp)
 
     // ---- split + store
     const double fs = 1.0 / (2.0 * (double)P);
     const bool fwd = mode == PDE_DCT_FWD;
-    for (int idx = threadIdx.x; idx < ns * (H + 1); idx += T) {
-        int s, k;
-        if (S == 1) {
-            s = 0;
-            k = idx;
-        } else if (AXIS == 1) {
-            s = idx / (H + 1);
-            k = idx - s * (H + 1);
-        } else {
-            k = idx / ns;
-            s = idx - k * ns;
-        }
+    constexpr int R1 = FirstRadix<RAD...>::value;
+    // outputs k and P - k of sequence s (k <= H); y_k = (A_k + conj(A_{P-k}))/2 - i e^{-i pi k / P} (A_k - conj(A_{P-k}))/2
+    auto split_one = [&](int sq, int k, const double2 *zq, double *dst) {
         const int k2 = P - k;
-        const double2 a = zsm[s * PS + PD::phys(DigitRev<P, RAD...>::pos(k))];
-        const double2 b = zsm[s * PS + PD::phys(DigitRev<P, RAD...>::pos(k == 0 ? 0 : k2))];
+        const int kk = k == 0 ? 0 : k2;
+        // digit-reversed position; its first-level block number is the lowest digit, so phys() needs no division
+        const double2 a = zq[DigitRev<P, RAD...>::pos(k) + k % R1];
+        const double2 b = zq[DigitRev<P, RAD...>::pos(kk) + kk % R1];
         const double2 cs = __ldg(CS + k);
         const double sr = a.x + b.x, dr = a.x - b.x, si = a.y + b.y;
-        double yk = 0.5 * (sr + cs.x * si - cs.y * dr);
-        double yk2 = 0.5 * (sr - cs.x * si + cs.y * dr);
-        if (fwd) {
-            yk *= (k == 0 ? fs : ((k & 1) ? -2.0 * fs : 2.0 * fs));
-            yk2 *= (k2 == P ? fs : ((k2 & 1) ? -2.0 * fs : 2.0 * fs));
+        // forward scale: 1/(2P) at the ends, +-1/P inside (the sign is (-1)^k, and P - k has the parity of k)
+        const double h = fwd ? (k == 0 ? 0.5 * fs : ((k & 1) ? -fs : fs)) : 0.5;
+        const double t = cs.x * si - cs.y * dr;
+        const double yk = h * (sr + t), yk2 = h * (sr - t);
+        if (AXIS == 1) {
+            if (k < n_out) dst[k] = yk;
+            if (k2 != k && k2 < n_out) dst[k2] = yk2;
+        } else {
+            if (k < n_out) dst[(long)k * (int)ldy] = yk;
+            if (k2 != k && k2 < n_out) dst[(long)k2 * (int)ldy] = yk2;
         }
-        double *dst = AXIS == 1 ? y + (long)(q0 + s) * ldy : y + q0 + s;
-        const long ds = AXIS == 1 ? 1 : ldy;
-        if (k < n_out) dst[k * ds] = yk;
-        if (k2 != k && k2 < n_out) dst[k2 * ds] = yk2;
+        (void)sq;
+    };
+    if (ns == S) {
+        static_assert((S * H) % T == 0, "S * P / 2 must be a multiple of T");
+        static_assert(AXIS == 1 ? (H % T == 0 || T % H == 0) : (H % (T / S) == 0), "thread mapping (split)");
+        constexpr int ITER = S * H / T;
+        constexpr int C = AXIS == 1 ? (H % T == 0 ? T : H) : T / S;
+        constexpr int SPI = AXIS == 1 ? (H % T == 0 ? 0 : T / H) : 0;
+        const int tk = AXIS == 1 ? (int)threadIdx.x % C : (int)threadIdx.x / S;
+        const int ts = AXIS == 1 ? (int)threadIdx.x / C : (int)threadIdx.x % S;
+        const double2 *tz = zsm + ts * PS;
+        double *tdst = AXIS == 1 ? y + (long)(q0 + ts) * (int)ldy : y + q0 + ts;
+        static_for<0, ITER>([&](auto ic) {
+            constexpr int it = decltype(ic)::value;
+            constexpr int sc = AXIS == 1 ? (H % T == 0 ? it / (H / T) : it * SPI) : 0;
+            constexpr int kc = AXIS == 1 ? (H % T == 0 ? (it % (H / T)) * T : 0) : it * C;
+            split_one(sc, kc + tk, tz + sc * PS, AXIS == 1 ? tdst + (long)sc * (int)ldy : tdst);
+        });
+        if (threadIdx.x < S) {                      // k = H (its partner is itself)
+            const int sq = threadIdx.x;
+            split_one(sq, H, zsm + sq * PS, AXIS == 1 ? y + (long)(q0 + sq) * (int)ldy : y + q0 + sq);
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < ns * (H + 1); idx += T) {
+            int sq, k;
+            if (AXIS == 1) {
+                sq = idx / (H + 1);
+                k = idx - sq * (H + 1);
+            } else {
+                k = idx / ns;
+                sq = idx - k * ns;
+            }
+            split_one(sq, k, zsm + sq * PS, AXIS == 1 ? y + (long)(q0 + sq) * (int)ldy : y + q0 + sq);
+        }
     }
 }
 
@@ -245,13 +361,25 @@ static int launch_fft_t(const FftDctPlan *p, int mode, int njobs, const DctPtrs 
     auto kern = k_dct_fft_t<P, S, T, AXIS, RAD...>;
     constexpr int M1 = P / FirstRadix<RAD...>::value;
     constexpr size_t smem = (size_t)S * Pad<P, M1>::SEQ * 16;
+    if (!p->Wp) {
+        std::vector<double2> tab;
+        build_pass_tables<RAD...>(P, P, tab);
+        double2 *d = nullptr;
+        PDE_CUDA(cudaMalloc(&d, sizeof(double2) * tab.size()));
+        PDE_CUDA(cudaMemcpy(d, tab.data(), sizeof(double2) * tab.size(), cudaMemcpyHostToDevice));
+        const_cast<FftDctPlan *>(p)->Wp = d;
+    }
     static bool attr = false;
     if (!attr) {
-        // enough shared memory for 4 CTAs (or as many as fit), the rest stays L1 for the twiddle table
+        // Shared-memory carve-out: room for up to 3 CTAs, and never more than needed -- what is left of the
+        // 256 KB is L1, which has to hold the twiddle tables (16 P bytes).  The S = 4 axis-0 CTAs need
+        // 193 KB + 1 KB: asking for 100 % left a 28 KB L1 that thrashed (0.31 ms); the 196 KB configuration
+        // leaves 60 KB.
         {
-            const int want = (int)(smem + 1024) * 3;
-            const int pct = want >= 227 * 1024 ? 100 : (want * 100 + 227 * 1024 - 1) / (227 * 1024);
-            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            const int per_cta = (int)smem + 1024;
+            const int fit = 227 * 1024 / per_cta;
+            const int want = per_cta * (fit < 3 ? fit : 3);
+            cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, want * 100 / (228 * 1024));
         }
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
@@ -260,8 +388,11 @@ static int launch_fft_t(const FftDctPlan *p, int mode, int njobs, const DctPtrs 
         }
         attr = true;
     }
+    // (Tried: launching the axis-0 CTAs as clusters of 2/4/8 so that the four 32-byte sectors of a line are
+    // requested close in time, and other shared-memory carve-outs: no effect once the row pitch of the arrays
+    // is not a multiple of 2 KB.  With a 16 KB pitch the axis-0 time is erratic, 0.2 .. 0.66 ms.)
     dim3 grid(ceil_div(batch, S), njobs);
-    kern<<<grid, T, smem, st>>>(p->W, p->CS, mode, ptrs, ldx, n_in, ldy, n_out, batch);
+    kern<<<grid, T, smem, st>>>(p->Wp, p->CS, mode, ptrs, ldx, n_in, ldy, n_out, batch);
     return after_launch("pde_dct1(fft, specialised)");
 }
 

@@ -10,7 +10,10 @@ from pypde_b200 import ops, Base  # noqa: E402
 
 L, nb = 3073, 2048
 plan = ops.DctPlan.get(L)
-x = torch.randn((L, nb), dtype=torch.float64, device="cuda")
+# row pitch padded by 64 bytes like the stepper's work arrays (fast_stepper._new): a 16 KB pitch maps a whole
+# column strip onto a few HBM channels and makes the axis-0 timing erratic (0.2 .. 0.66 ms run to run)
+x = torch.zeros((L, nb + 8), dtype=torch.float64, device="cuda")[:, :nb]
+x.copy_(torch.randn((L, nb), dtype=torch.float64, device="cuda"))
 xt = x.T.contiguous()
 for _ in range(3):
     y0 = ops.dct1(plan, ops.BWD, x, axis=0)
@@ -24,15 +27,31 @@ for _ in range(2):
     b.from_chebyshev(u, axis=0)
     b.from_chebyshev(u, axis=1)
 torch.cuda.synchronize()
+from pypde_b200 import _cabi as C  # noqa: E402
+
+
+def padded(r, c):
+    return torch.zeros((r, c + 8), dtype=torch.float64, device="cuda")[:, :c]
+
+
 for axis, arr in ((0, x), (1, xt)):
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10):
-        ops.dct1(plan, ops.BWD, arr, axis=axis)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
-    print("dct axis %d: %.3f ms  %.1f GB/s algorithmic" % (axis, ms, 16.0 * L * nb / ms / 1e6))
+    out = padded(*arr.shape)                    # same shape: L -> L along the transform axis
+    ldx, ldy = arr.stride(0), out.stride(0)
+
+    def run():
+        C.check(C.lib().pde_dct1(plan.handle, ops.BWD, C.p(arr), ldx, L, C.p(out), ldy, L, nb, axis, C.stream()))
+
+    for rep in range(3):
+        run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            run()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print("dct axis %d: %.3f ms  %.1f GB/s algorithmic" % (axis, ms, 16.0 * L * nb / ms / 1e6))
 
 from pypde_b200 import PlanLHS
 import numpy as np
