@@ -12,23 +12,42 @@ struct StencilJobs {
     pde_stencil_job j[PDE_MAX_JOBS];
 };
 
+// The three pointwise kernels below compute RPT rows per thread and issue EVERY load of those rows before
+// the first use.  The first versions tested the loaded coefficient (skip zero diagonals entries) before
+// loading the operand, one tap after the other: four serialised memory round trips per output, 1.8 TB/s.
+// The selects keep the arithmetic of the reference expression exactly (same products, same order of sums,
+// zero coefficients skipped).
+constexpr int RPT = 4;
+
 __global__ void k_to_cheb_multi(StencilJobs jobs, int axis)
 {
     const pde_stencil_job &jb = jobs.j[blockIdx.z];
     const int n0 = axis == 0 ? jb.n_out : jb.batch, n1 = axis == 0 ? jb.batch : jb.n_out;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= n0 || j >= n1) return;
-    const int k = axis == 0 ? i : j;
+    const int i0 = blockIdx.y * (blockDim.y * RPT) + threadIdx.y;
+    if (j >= n1) return;
     const long step = axis == 0 ? jb.ldv : 1;
-    const double *vp = jb.v + (long)i * jb.ldv + j;
-    double acc = 0.0;
-    if (k >= 2 && k - 2 < jb.M) {
-        const double sk = __ldg(jb.s + k - 2);
-        if (sk != 0.0) acc = sk * vp[-2 * step];
+    double sk[RPT], vm[RPT], v0[RPT];
+    bool lo[RPT], hi[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const int i = i0 + r * blockDim.y;
+        const int k = axis == 0 ? i : j;
+        const double *vp = jb.v + (long)i * jb.ldv + j;
+        lo[r] = i < n0 && k >= 2 && k - 2 < jb.M;
+        hi[r] = i < n0 && k < jb.M;
+        sk[r] = lo[r] ? __ldg(jb.s + k - 2) : 0.0;
+        vm[r] = lo[r] ? vp[-2 * step] : 0.0;
+        v0[r] = hi[r] ? vp[0] : 0.0;
     }
-    if (k < jb.M) acc = acc + vp[0];
-    jb.u[(long)i * jb.ldu + j] = acc;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const int i = i0 + r * blockDim.y;
+        if (i >= n0) continue;
+        double acc = (lo[r] && sk[r] != 0.0) ? sk[r] * vm[r] : 0.0;
+        if (hi[r]) acc = acc + v0[r];
+        jb.u[(long)i * jb.ldu + j] = acc;
+    }
 }
 
 struct BandJobs {
@@ -36,25 +55,41 @@ struct BandJobs {
     pde_band_job j[PDE_MAX_JOBS];
 };
 
-__global__ void k_banded_multi(BandJobs jobs, int axis)
+constexpr int RPB = 2;       // rows per thread of the banded product (4 needs 93 registers and was slower)
+
+template <int MAXD>
+__global__ void __launch_bounds__(256, 4) k_banded_multi(BandJobs jobs, int axis)
 {
     const pde_band_job &jb = jobs.j[blockIdx.z];
     const int n0 = axis == 0 ? jb.n_out : jb.batch, n1 = axis == 0 ? jb.batch : jb.n_out;
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= n0 || j >= n1) return;
-    const int r = axis == 0 ? i : j;
-    double acc = 0.0;
-    for (int d = 0; d < jb.ndiag; ++d) {
-        const int c = r + jb.off[d];
-        if (c < 0 || c >= jb.n_in) continue;
-        const double a = __ldg(jb.diags + (long)d * jb.n_out + r);
-        if (a == 0.0) continue;
-        const double xv = axis == 0 ? jb.x[(long)c * jb.ldx + j] : jb.x[(long)i * jb.ldx + c];
-        acc = acc + a * xv;
+    const int i0 = blockIdx.y * (blockDim.y * RPB) + threadIdx.y;
+    if (j >= n1) return;
+    double a[RPB][MAXD], xv[RPB][MAXD], yo[RPB];
+    bool ok[RPB][MAXD];
+#pragma unroll
+    for (int r = 0; r < RPB; ++r) {
+        const int i = i0 + r * blockDim.y;
+        const int row = axis == 0 ? i : j;
+#pragma unroll
+        for (int d = 0; d < MAXD; ++d) {
+            const int c = row + (d < jb.ndiag ? jb.off[d] : 0);
+            ok[r][d] = i < n0 && d < jb.ndiag && c >= 0 && c < jb.n_in;
+            a[r][d] = ok[r][d] ? __ldg(jb.diags + (long)d * jb.n_out + row) : 0.0;
+            xv[r][d] = ok[r][d] ? (axis == 0 ? jb.x[(long)c * jb.ldx + j] : jb.x[(long)i * jb.ldx + c]) : 0.0;
+        }
+        yo[r] = (jb.accumulate && i < n0) ? jb.y[(long)i * jb.ldy + j] : 0.0;
     }
-    double *yp = jb.y + (long)i * jb.ldy + j;
-    *yp = jb.accumulate ? *yp + acc : acc;
+#pragma unroll
+    for (int r = 0; r < RPB; ++r) {
+        const int i = i0 + r * blockDim.y;
+        if (i >= n0) continue;
+        double acc = 0.0;
+#pragma unroll
+        for (int d = 0; d < MAXD; ++d)
+            if (ok[r][d] && a[r][d] != 0.0) acc = acc + a[r][d] * xv[r][d];
+        jb.y[(long)i * jb.ldy + j] = jb.accumulate ? yo[r] + acc : acc;
+    }
 }
 
 struct LincombJobs {
@@ -66,15 +101,30 @@ __global__ void k_lincomb_multi(LincombJobs jobs)
 {
     const pde_lincomb_job &jb = jobs.j[blockIdx.z];
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y * blockDim.y + threadIdx.y;
-    if (i >= jb.n0 || j >= jb.n1) return;
-    double acc = 0.0;
-    for (int t = 0; t < jb.nterm; ++t) {
-        const double xv = jb.x[t][(long)i * jb.ldx[t] + j];
-        const double term = jb.coef[t] == 1.0 ? xv : jb.coef[t] * xv;
-        acc = t == 0 ? term : acc + term;
+    const int i0 = blockIdx.y * (blockDim.y * RPT) + threadIdx.y;
+    if (j >= jb.n1) return;
+    constexpr int MAXT = 4;
+    double xv[RPT][MAXT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const int i = i0 + r * blockDim.y;
+#pragma unroll
+        for (int t = 0; t < MAXT; ++t)
+            xv[r][t] = (i < jb.n0 && t < jb.nterm) ? jb.x[t][(long)i * jb.ldx[t] + j] : 0.0;
     }
-    jb.y[(long)i * jb.ldy + j] = acc;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const int i = i0 + r * blockDim.y;
+        if (i >= jb.n0) continue;
+        double acc = 0.0;
+#pragma unroll
+        for (int t = 0; t < MAXT; ++t) {
+            if (t >= jb.nterm) break;
+            const double term = jb.coef[t] == 1.0 ? xv[r][t] : jb.coef[t] * xv[r][t];
+            acc = t == 0 ? term : acc + term;
+        }
+        jb.y[(long)i * jb.ldy + j] = acc;
+    }
 }
 
 __global__ void k_conv_products(long n, double b, double c, const double *__restrict__ u,
@@ -183,7 +233,7 @@ int pde_to_cheb_multi(int axis, int njobs, const pde_stencil_job *jobs, void *st
         m1 = n1 > m1 ? n1 : m1;
     }
     if (m0 <= 0 || m1 <= 0) return PDE_OK;
-    dim3 block(64, 4), grid(ceil_div(m1, 64), ceil_div(m0, 4), njobs);
+    dim3 block(64, 4), grid(ceil_div(m1, 64), ceil_div(m0, 4 * RPT), njobs);
     k_to_cheb_multi<<<grid, block, 0, as_stream(stream)>>>(sj, axis);
     return after_launch("pde_to_cheb_multi");
 }
@@ -194,17 +244,19 @@ int pde_banded_multi(int axis, int njobs, const pde_band_job *jobs, void *stream
     PDE_REQUIRE(axis == 0 || axis == 1, "axis");
     BandJobs bj{};
     bj.njobs = njobs;
-    int m0 = 0, m1 = 0;
+    int m0 = 0, m1 = 0, maxd = 0;
     for (int j = 0; j < njobs; ++j) {
         PDE_REQUIRE(jobs[j].ndiag >= 1 && jobs[j].ndiag <= 8, "1..8 diagonals");
+        maxd = jobs[j].ndiag > maxd ? jobs[j].ndiag : maxd;
         bj.j[j] = jobs[j];
         const int n0 = axis == 0 ? jobs[j].n_out : jobs[j].batch, n1 = axis == 0 ? jobs[j].batch : jobs[j].n_out;
         m0 = n0 > m0 ? n0 : m0;
         m1 = n1 > m1 ? n1 : m1;
     }
     if (m0 <= 0 || m1 <= 0) return PDE_OK;
-    dim3 block(64, 4), grid(ceil_div(m1, 64), ceil_div(m0, 4), njobs);
-    k_banded_multi<<<grid, block, 0, as_stream(stream)>>>(bj, axis);
+    dim3 block(64, 4), grid(ceil_div(m1, 64), ceil_div(m0, 4 * RPB), njobs);
+    if (maxd <= 4) k_banded_multi<4><<<grid, block, 0, as_stream(stream)>>>(bj, axis);
+    else k_banded_multi<8><<<grid, block, 0, as_stream(stream)>>>(bj, axis);
     return after_launch("pde_banded_multi");
 }
 
@@ -221,7 +273,7 @@ int pde_lincomb_multi(int njobs, const pde_lincomb_job *jobs, void *stream)
         m1 = jobs[j].n1 > m1 ? jobs[j].n1 : m1;
     }
     if (m0 <= 0 || m1 <= 0) return PDE_OK;
-    dim3 block(64, 4), grid(ceil_div(m1, 64), ceil_div(m0, 4), njobs);
+    dim3 block(64, 4), grid(ceil_div(m1, 64), ceil_div(m0, 4 * RPT), njobs);
     k_lincomb_multi<<<grid, block, 0, as_stream(stream)>>>(lj);
     return after_launch("pde_lincomb_multi");
 }
