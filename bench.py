@@ -264,6 +264,7 @@ def run_ensemble(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
+        quiet_nccl()
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from pypde_b200 import _cabi
     from pypde_b200.navier.ensemble import Ensemble
@@ -334,6 +335,12 @@ def run_ensemble(args):
         dist.destroy_process_group()
 
 
+def quiet_nccl():
+    """The image exports NCCL_DEBUG=VERSION, which prints a banner on stdout next to the JSON line."""
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"
+
+
 def run_gpu(args, cfg):
     import torch
     import torch.distributed as dist
@@ -344,6 +351,7 @@ def run_gpu(args, cfg):
     torch.cuda.set_device(local)
     slab = world > 1
     if slab:
+        quiet_nccl()
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         # Capturing the NCCL transposes in the CUDA graph works (rbc512 x2: 2.74 vs 3.03 ms/step) but the
         # process then hung in teardown on this stack, so the multi-GPU step is launched eagerly.
@@ -418,8 +426,7 @@ def run_gpu(args, cfg):
         for h, t in zip(host_out, state_tensors):
             h.copy_(t, non_blocking=True)
         torch.cuda.synchronize()
-        for hi, ho in zip(host_in, host_out):
-            hi.copy_(ho)
+        host_in, host_out = host_out, host_in      # the next step's input is this step's host result
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1)) / e2e_steps

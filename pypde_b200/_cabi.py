@@ -14,7 +14,7 @@ import numpy as np
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "libpypde_b200.so")
+LIB_PATH = os.environ.get("PYPDE_B200_LIB") or os.path.join(_HERE, "_lib", "libpypde_b200.so")
 
 _c_dp = ctypes.c_void_p
 _c_long = ctypes.c_long

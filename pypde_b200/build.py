@@ -19,6 +19,7 @@ LIB = os.path.join(OUT, "libpypde_b200.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
+COMMON += os.environ.get("PDE_NVCC_EXTRA", "").split()      # developer experiments (e.g. -DPDE_SW_KC=8)
 # banded.cu keeps the Fortran operation order (bit parity with the oracle): no FMA contraction
 PER_FILE = {"banded.cu": ["--fmad=false"], "batched.cu": ["--fmad=false"]}
 

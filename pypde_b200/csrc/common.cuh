@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <string>
 #include <atomic>
+#include <type_traits>
 
 #include "pypde_b200.h"
 
@@ -48,5 +49,17 @@ inline int after_launch(const char *what)
 int sm_count();
 
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
+
+#ifdef __CUDACC__
+// compile-time loop: f(std::integral_constant<int, I>) for I in [I0, N)
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F &&f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+#endif
 
 }  // namespace pde

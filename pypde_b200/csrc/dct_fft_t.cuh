@@ -9,19 +9,8 @@
 // shared-memory round trips instead of six) and the digit reversal is arithmetic.
 // Same algorithm and data flow as k_dct_fft (see dct_fft.cu).
 #pragma once
-#include <type_traits>
 
 namespace pde {
-
-// compile-time loop: f(std::integral_constant<int, I>) for I in [I0, N)
-template <int I, int N, typename F>
-__device__ __forceinline__ void static_for(F &&f)
-{
-    if constexpr (I < N) {
-        f(std::integral_constant<int, I>{});
-        static_for<I + 1, N>(f);
-    }
-}
 
 template <>
 __device__ __forceinline__ void dft<8>(double2 *a)
