@@ -3,6 +3,7 @@
 // Compiled with --fmad=false: every product and sum is rounded separately, like the
 // NumPy / SciPy expressions of the reference.
 #include "common.cuh"
+#include <cmath>
 #include "sweeps.cuh"
 
 namespace pde {
@@ -196,11 +197,18 @@ int pde_sweep(int op, int axis, int n, int njobs, const pde_sweep_job *jobs, voi
     for (int j = 0; j < njobs; ++j) sj.j[j] = jobs[j];
     cudaStream_t st = as_stream(stream);
     // FULL instantiations (no run-time feature tests) when every job supplies all optional tables
-    bool full = true;
+    bool full = true, pow2 = true;
     for (int j = 0; j < njobs; ++j) {
         const pde_sweep_job &jb = jobs[j];
         switch (op) {
-        case PDE_SWEEP_DIFF: full = full && jb.flag != 0; break;
+        case PDE_SWEEP_DIFF: {
+            full = full && jb.flag != 0;
+            // x / 2^k == x * 2^-k bit for bit: the division sequence becomes one multiplication
+            int ex = 0;
+            const double sc = jb.flag != 0 ? jb.sc : 1.0;
+            pow2 = pow2 && sc > 0.0 && std::isfinite(sc) && std::frexp(sc, &ex) == 0.5 && ex > -1000 && ex < 1000;
+            break;
+        }
         case PDE_SWEEP_TDMA_FWD: full = full && jb.tab[0] && jb.tab[4] && jb.in[1]; break;
         case PDE_SWEEP_FDMA_BWD: full = full && jb.tab[4]; break;
         default: break;
@@ -208,7 +216,13 @@ int pde_sweep(int op, int axis, int n, int njobs, const pde_sweep_job *jobs, voi
     }
 #define PDE_SW(OP, what) (full ? launch_sweep<OP<true>>(sj, axis, st, what) : launch_sweep<OP<false>>(sj, axis, st, what))
     switch (op) {
-    case PDE_SWEEP_DIFF: return PDE_SW(DiffDesc, "pde_sweep(diff)");
+    case PDE_SWEEP_DIFF:
+        if (pow2) {
+            for (int j = 0; j < njobs; ++j)
+                if (sj.j[j].flag == 0) sj.j[j].sc = 1.0;
+            return launch_sweep<DiffDesc<true, true>>(sj, axis, st, "pde_sweep(diff, pow2 scale)");
+        }
+        return PDE_SW(DiffDesc, "pde_sweep(diff)");
     case PDE_SWEEP_TDMA_FWD: return PDE_SW(TdmaFwd, "pde_sweep(tdma fwd)");
     case PDE_SWEEP_TDMA_BWD: return launch_sweep<TdmaBwd<true>>(sj, axis, st, "pde_sweep(tdma bwd)");
     case PDE_SWEEP_FDMA_FWD: return launch_sweep<FdmaFwd<true>>(sj, axis, st, "pde_sweep(fdma fwd)");

@@ -71,14 +71,55 @@ __device__ __forceinline__ void dft<16>(double2 *a)
     }
 }
 
+template <>
+__device__ __forceinline__ void dft<12>(double2 *a)
+{
+    // n = n0 + 3 n1 (n0 < 3, n1 < 4), k = k1 + 4 k0:  T[n0][k1] = DFT4_{n1} a[n0 + 3 n1];  U = T * W12^{n0 k1};
+    // X[k1 + 4 k0] = DFT3_{n0} U[n0][k1].  3072 = 16 * 16 * 12: the last pass (no twiddles) replaces the
+    // radix-4 and radix-3 passes, three shared-memory round trips instead of four.
+    const double c = 0.86602540378443864676, h = 0.5;                 // cos, sin(pi/6)
+    double2 t[3][4];
+#pragma unroll
+    for (int n0 = 0; n0 < 3; ++n0) {
+        double2 v[4] = {a[n0], a[n0 + 3], a[n0 + 6], a[n0 + 9]};
+        dft<4>(v);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) t[n0][k1] = v[k1];
+    }
+    // W12^m = exp(-i pi m / 6):  m = 1: (c, -h);  2: (h, -c);  3: -i;  4: (-h, -c);  6: -1
+    t[1][1] = make_double2(c * t[1][1].x + h * t[1][1].y, c * t[1][1].y - h * t[1][1].x);
+    t[1][2] = make_double2(h * t[1][2].x + c * t[1][2].y, h * t[1][2].y - c * t[1][2].x);
+    t[1][3] = mul_mi(t[1][3]);
+    t[2][1] = make_double2(h * t[2][1].x + c * t[2][1].y, h * t[2][1].y - c * t[2][1].x);
+    t[2][2] = make_double2(c * t[2][2].y - h * t[2][2].x, -(c * t[2][2].x + h * t[2][2].y));
+    t[2][3] = make_double2(-t[2][3].x, -t[2][3].y);
+#pragma unroll
+    for (int k1 = 0; k1 < 4; ++k1) {
+        double2 v[3] = {t[0][k1], t[1][k1], t[2][k1]};
+        dft<3>(v);
+#pragma unroll
+        for (int k0 = 0; k0 < 3; ++k0) a[k1 + 4 * k0] = v[k0];
+    }
+}
+
 // Shared-memory layout of one sequence: logical index i lives at i + i / M1 (M1 = P / first radix):
 // one pad element after each first-level block.  The split step reads the digit-reversed FFT output
 // with stride M1 between consecutive k; M1 is a multiple of 8 elements (= all banks), so without the
 // pad those reads were 8-way bank conflicts (ncu: 48 % of the shared wavefronts).
-template <int P, int M1>
+//
+// SP extra elements follow each sequence.  An axis-0 CTA holds S adjacent columns and its load / split
+// phases map a quarter-warp to (8 / S elements) x (S sequences): with a sequence pitch that is a multiple
+// of 8 elements the S lanes of one element hit the same bank group (4-way conflicts on 2 of the ~11
+// shared-memory sweeps of the kernel); a pitch of 8 / S (mod 8) spreads them over all eight.
+template <int P, int M1, int SP = 0>
 struct Pad {
-    static constexpr int SEQ = P + P / M1;                 // padded sequence length
+    static constexpr int SEQ = P + P / M1 + SP;            // padded sequence length
     __device__ __forceinline__ static int phys(int i) { return i + i / M1; }
+};
+template <int P, int M1, int S, int AXIS>
+struct SeqPad {
+    static constexpr int value =
+        (AXIS != 0 || S <= 1 || 8 % S != 0) ? 0 : ((8 / (S > 0 ? S : 1) - (P + P / M1) % 8) % 8 + 8) % 8;
 };
 
 // Twiddles of a DIF pass.  WOFF < 0: the plain table W[t] = exp(-2 pi i t / P), read with stride (Bluestein
@@ -86,22 +127,39 @@ struct Pad {
 // W + WOFF: consecutive lanes (consecutive j) read consecutive entries.  ncu on the strided version showed the
 // L1TEX pipe 77 % busy -- a warp's request for W[j * r] touches up to 60 cache lines in the first pass, as
 // many L1 cycles as all shared-memory traffic of the pass; same values, so results are bit-identical.
-template <int WOFF, int P, int M1, int NCUR, int S, int T, int R>
+//
+// Thread -> butterfly map of the passes after the first.  The butterflies of a pass are (block, j) with
+// block < P / NCUR and j < M.  Walking j fastest (the obvious map) puts the 8 lanes of a quarter-warp on
+// addresses blk * NCUR + j + r * M with M = 12, 3, 8, ... : 2- to 8-way bank conflicts (tools/sim_fft_banks.py:
+// x1.33 / x2 on passes 2 / 3 of P = 3072, x8 on the radix-8 pass of P = 2048).  Instead consecutive
+// butterflies walk the FIRST-LEVEL blocks (pitch M1 + 1 elements, odd, so 8 lanes hit 8 bank groups), then
+// the blocks inside a first-level block, and j is the slowest index (its twiddles become warp broadcasts).
+template <int WOFF, int P, int M1, int NCUR, int S, int T, int R, int SP = 0>
 __device__ __forceinline__ void dif_pass_t(double2 *z, const double2 *__restrict__ W)
 {
     constexpr int M = NCUR / R, PER_SEQ = P / R, TOTAL = S * PER_SEQ, TWS = P / NCUR;
-    constexpr int PS = Pad<P, M1>::SEQ;
+    constexpr int PS = Pad<P, M1, SP>::SEQ;
     constexpr int RS = NCUR == P ? M + 1 : M;              // first pass: stride M1 + 1 (padded)
+    constexpr int R1 = P / M1;                             // first radix = number of first-level blocks
+    constexpr int NBLK = P / NCUR;                         // blocks of this level per sequence
+    static_assert(NCUR == P || NBLK % R1 == 0, "levels nest inside the first-level blocks");
 #pragma unroll
     for (int b0 = 0; b0 < TOTAL; b0 += T) {
         const int b = b0 + threadIdx.x;
         if ((TOTAL % T) != 0 && b >= TOTAL) break;
         const int s = b / PER_SEQ;
         const int bb = b - s * PER_SEQ;
-        const int blk = bb / M;
-        const int j = bb - blk * M;
-        const int i0 = blk * NCUR + j;
-        double2 *p = z + s * PS + (NCUR == P ? i0 : Pad<P, M1>::phys(i0));
+        int j, off;                                        // off = padded position of element (blk, j)
+        if (NCUR == P) {
+            j = bb;
+            off = bb;
+        } else {
+            j = bb / NBLK;
+            const int bi = bb - j * NBLK;
+            const int first = bi % R1, inner = bi / R1;
+            off = first * (M1 + 1) + inner * NCUR + j;
+        }
+        double2 *p = z + s * PS + off;
         double2 a[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) a[r] = p[r * RS];
@@ -116,19 +174,19 @@ __device__ __forceinline__ void dif_pass_t(double2 *z, const double2 *__restrict
     }
 }
 
-template <int WOFF, int P, int M1, int NCUR, int S, int T, int R, int... Rest>
+template <int SP, int WOFF, int P, int M1, int NCUR, int S, int T, int R, int... Rest>
 struct DifPassesW {
     __device__ __forceinline__ static void run(double2 *z, const double2 *__restrict__ W)
     {
-        dif_pass_t<WOFF, P, M1, NCUR, S, T, R>(z, W);
+        dif_pass_t<WOFF, P, M1, NCUR, S, T, R, SP>(z, W);
         __syncthreads();
         constexpr int NEXT = WOFF < 0 ? -1 : WOFF + (NCUR / R > 1 ? (R - 1) * (NCUR / R) : 0);
-        if constexpr (sizeof...(Rest) > 0) DifPassesW<NEXT, P, M1, NCUR / R, S, T, Rest...>::run(z, W);
+        if constexpr (sizeof...(Rest) > 0) DifPassesW<SP, NEXT, P, M1, NCUR / R, S, T, Rest...>::run(z, W);
     }
 };
 
 template <int P, int M1, int NCUR, int S, int T, int... RAD>
-struct DifPasses : DifPassesW<-1, P, M1, NCUR, S, T, RAD...> {
+struct DifPasses : DifPassesW<0, -1, P, M1, NCUR, S, T, RAD...> {
 };
 
 // host: the [r][j] tables of all passes, concatenated in pass order (offsets as in DifPassesW)
@@ -173,7 +231,7 @@ constexpr int fft_regs(int ctas, int T)
 }
 template <int P, int S, int T, int R1>
 struct FftRegs {
-    static constexpr int SMEM = S * Pad<P, P / R1>::SEQ * 16 + 1024;
+    static constexpr int SMEM = S * Pad<P, P / R1, 7>::SEQ * 16 + 1024;
     static constexpr int FIT = 227 * 1024 / SMEM;
     static constexpr int C3 = FIT < 1 ? 1 : (FIT > 3 ? 3 : FIT);
     static constexpr int CTAS = fft_regs(C3, T) >= 96 ? C3 : (C3 > 1 && fft_regs(C3 - 1, T) >= 96 ? C3 - 1 : 1);
@@ -194,7 +252,8 @@ k_dct_fft_t(const double2 *__restrict__ W, const double2 *__restrict__ CS, int m
     const double se = bwd ? 0.5 : 1.0, so = bwd ? -0.5 : 1.0;       // scale of even / odd interior inputs
     constexpr int H = P / 2;
     constexpr int M1 = P / FirstRadix<RAD...>::value;
-    using PD = Pad<P, M1>;
+    constexpr int SP = SeqPad<P, M1, S, AXIS>::value;
+    using PD = Pad<P, M1, SP>;
     constexpr int PS = PD::SEQ;
 
     // ---- load: z_m = (e_2m, e_2m+1); m < P/2: (x_2m, x_2m+1); m >= P/2: (x_{2P-2m}, x_{2P-2m-1})
@@ -280,7 +339,7 @@ k_dct_fft_t(const double2 *__restrict__ W, const double2 *__restrict__ CS, int m
         }
     }
     __syncthreads();
-    DifPassesW<0, P, M1, P, S, T, RAD...>::run(zsm, W);          // W: per-pass [r][j] tables (p->Wp)
+    DifPassesW<SP, 0, P, M1, P, S, T, RAD...>::run(zsm, W);      // W: per-pass [r][j] tables (p->Wp)
 
     // ---- split + store
     const double fs = 1.0 / (2.0 * (double)P);
@@ -349,7 +408,7 @@ static int launch_fft_t(const FftDctPlan *p, int mode, int njobs, const DctPtrs 
 {
     auto kern = k_dct_fft_t<P, S, T, AXIS, RAD...>;
     constexpr int M1 = P / FirstRadix<RAD...>::value;
-    constexpr size_t smem = (size_t)S * Pad<P, M1>::SEQ * 16;
+    constexpr size_t smem = (size_t)S * Pad<P, M1, SeqPad<P, M1, S, AXIS>::value>::SEQ * 16;
     if (!p->Wp) {
         std::vector<double2> tab;
         build_pass_tables<RAD...>(P, P, tab);
@@ -394,6 +453,23 @@ static int dispatch_fft_t(const FftDctPlan *p, int mode, int njobs, const DctPtr
 {
 #define PDE_FFT_CASE(PP, SS, TT, ...)                                                                     \
     case PP: return launch_fft_t<PP, SS, TT, AXIS, __VA_ARGS__>(p, mode, njobs, ptrs, ldx, n_in, ldy, n_out, batch, st);
+    // 3 * 2^k with a final radix-12 pass (three shared-memory round trips instead of four); PDE_FFT_RADIX12=0
+    // selects the radix-4 + radix-3 tail for comparison
+    static const bool radix12 = !(getenv("PDE_FFT_RADIX12") && atoi(getenv("PDE_FFT_RADIX12")) == 0);
+    if (radix12) {
+        if (AXIS == 0) {
+            switch (p->P) {
+                PDE_FFT_CASE(1536, 4, 384, 16, 8, 12)
+                PDE_FFT_CASE(3072, 4, 384, 16, 16, 12)
+            default: break;
+            }
+        }
+        switch (p->P) {
+            PDE_FFT_CASE(1536, 2, 192, 16, 8, 12)
+            PDE_FFT_CASE(3072, 1, 192, 16, 16, 12)
+        default: break;
+        }
+    }
     if (AXIS == 0) {
         // strided sequences: >= 4 adjacent columns per CTA so that every global access is a full
         // 32-byte sector (S = 1 measured 0.25 ms vs 0.14 ms for the contiguous axis at P = 3072)

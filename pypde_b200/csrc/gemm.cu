@@ -5,13 +5,17 @@
 // (Hy, Qy: pypde/templates/poisson.py:93-108) and for the dense-matrix DCT-I of
 // small transform lengths.
 //
-// CTA tile 128 x 64 x 16, 8 warps (4 x 2), warp tile 32 x 32 = 4 x 4 DMMA tiles,
+// CTA tile (8 MI WM) x (8 NI WN) x 16 with 8 warps laid out WM x WN, warp tile = MI x NI DMMA tiles
+// (128 x 64 = 4 x 2 warps of 4 x 4 tiles; 128 x 56 = 8 x 1 warps of 2 x 7 tiles; 64 x 64; 32 x 64),
 // 3-stage cp.async ring in shared memory; smem rows are padded so that the
-// 64-bit fragment loads of a half-warp hit 16 distinct bank pairs.
+// 64-bit fragment loads of a half-warp hit 16 distinct bank pairs.  The tile shape is chosen per
+// problem to fill whole waves of 2 CTAs per SM: the Poisson projections of rbc2048 (2046 x 2046) are
+// 512 tiles of 128 x 64 = 1.73 waves on 148 SMs, but 592 tiles of 128 x 56 = exactly 2 waves (-12 %).
 // fp64 is the only tensor-core precision this path may use (parity <= 1e-12);
 // on B200 the DMMA pipe issues 64 FMA/clk/SM, the same peak as the DFMA pipe, so
 // the kernel is issue-bound on DMMA long before shared memory matters.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace pde {
 
@@ -72,16 +76,16 @@ __device__ __forceinline__ void load_tile_kmajor(double *sm, const double *g, lo
     }
 }
 
-// BK x BN tile of a row-major (n contiguous) matrix -> smem [BK][BPITCH_NN]
-template <bool VEC>
+// BK x BNT tile of a row-major (n contiguous) matrix -> smem [BK][BPITCH_NN]
+template <bool VEC, int BNT>
 __device__ __forceinline__ void load_tile_nmajor(double *sm, const double *g, long ld, int k0, int K, int n0,
                                                  int N)
 {
     if (VEC) {
-        constexpr int CHUNKS = BK * (BN / 2);
+        constexpr int CHUNKS = BK * (BNT / 2);
 #pragma unroll
         for (int c = threadIdx.x; c < CHUNKS; c += 256) {
-            const int kr = c / (BN / 2), nc = (c % (BN / 2)) * 2;
+            const int kr = c / (BNT / 2), nc = (c % (BNT / 2)) * 2;
             const int gk = k0 + kr, gn = n0 + nc;
             int bytes = 0;
             if (gk < K) bytes = gn + 1 < N ? 16 : (gn < N ? 8 : 0);
@@ -89,10 +93,10 @@ __device__ __forceinline__ void load_tile_nmajor(double *sm, const double *g, lo
             cp_async16(sm + kr * BPITCH_NN + nc, src, bytes);
         }
     } else {
-        constexpr int ELEMS = BK * BN;
+        constexpr int ELEMS = BK * BNT;
 #pragma unroll
         for (int c = threadIdx.x; c < ELEMS; c += 256) {
-            const int kr = c / BN, nc = c % BN;
+            const int kr = c / BNT, nc = c % BNT;
             const int gk = k0 + kr, gn = n0 + nc;
             const int bytes = (gk < K && gn < N) ? 8 : 0;
             const double *src = bytes ? g + (long)gk * ld + gn : g;
@@ -101,32 +105,34 @@ __device__ __forceinline__ void load_tile_nmajor(double *sm, const double *g, lo
     }
 }
 
-template <bool TB, bool VEC, int MI>
+template <bool TB, bool VEC, int MI, int NI, int WN>
 __global__ void __launch_bounds__(256, 2)
 k_gemm_f64(const double *__restrict__ A, long lda, const double *__restrict__ B, long ldb,
            double *__restrict__ C, long ldc, int M, int N, int K)
 {
-    constexpr int BM = 32 * MI;
+    constexpr int WM = 8 / WN;
+    constexpr int BM = WM * 8 * MI, BNT = WN * 8 * NI;
+    static_assert(BM <= 128 && BNT <= BN, "tile exceeds the shared-memory layout");
     constexpr int A_TILE = BM * APITCH;
     extern __shared__ __align__(16) double smem[];
     double *As = smem;
     double *Bs = smem + STAGES * A_TILE;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BNT;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wm = warp & 3, wn = warp >> 2;
+    const int wm = warp % WM, wn = warp / WM;
     const int lr = lane >> 2, lc = lane & 3;
 
-    double acc[MI][4][2];
+    double acc[MI][NI][2];
 #pragma unroll
     for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     const int KT = (K + BK - 1) / BK;
     auto load = [&](int kt, int stage) {
         load_tile_kmajor<BM, VEC>(As + stage * A_TILE, A, lda, m0, M, kt * BK, K);
-        if (TB) load_tile_kmajor<BN, VEC>(Bs + stage * B_TILE, B, ldb, n0, N, kt * BK, K);
-        else load_tile_nmajor<VEC>(Bs + stage * B_TILE, B, ldb, kt * BK, K, n0, N);
+        if (TB) load_tile_kmajor<BNT, VEC>(Bs + stage * B_TILE, B, ldb, n0, N, kt * BK, K);
+        else load_tile_nmajor<VEC, BNT>(Bs + stage * B_TILE, B, ldb, kt * BK, K, n0, N);
     };
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
@@ -140,20 +146,20 @@ k_gemm_f64(const double *__restrict__ A, long lda, const double *__restrict__ B,
         if (nk < KT) load(nk, nk % STAGES);
         cp_async_commit();
         const double *as = As + (kt % STAGES) * A_TILE + (wm * 8 * MI + lr) * APITCH + lc;
-        const double *bs = TB ? Bs + (kt % STAGES) * B_TILE + (wn * 32 + lr) * APITCH + lc
-                              : Bs + (kt % STAGES) * B_TILE + lc * BPITCH_NN + wn * 32 + lr;
+        const double *bs = TB ? Bs + (kt % STAGES) * B_TILE + (wn * 8 * NI + lr) * APITCH + lc
+                              : Bs + (kt % STAGES) * B_TILE + lc * BPITCH_NN + wn * 8 * NI + lr;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
-            double a[MI], b[4];
+            double a[MI], b[NI];
 #pragma unroll
             for (int i = 0; i < MI; ++i) a[i] = as[i * 8 * APITCH + kk * 4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < NI; ++j)
                 b[j] = TB ? bs[j * 8 * APITCH + kk * 4] : bs[kk * 4 * BPITCH_NN + j * 8];
 #pragma unroll
             for (int i = 0; i < MI; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < NI; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
     }
     cp_async_wait<0>();
@@ -163,8 +169,8 @@ k_gemm_f64(const double *__restrict__ A, long lda, const double *__restrict__ B,
         const int row = m0 + wm * 8 * MI + i * 8 + lr;
         if (row >= M) continue;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int col = n0 + wn * 32 + j * 8 + lc * 2;
+        for (int j = 0; j < NI; ++j) {
+            const int col = n0 + wn * 8 * NI + j * 8 + lc * 2;
             double *cp = C + (long)row * ldc + col;
             if (VEC && col + 1 < N) {
                 *reinterpret_cast<double2 *>(cp) = make_double2(acc[i][j][0], acc[i][j][1]);
@@ -176,50 +182,75 @@ k_gemm_f64(const double *__restrict__ A, long lda, const double *__restrict__ B,
     }
 }
 
+// tile shapes: {BM, BN, MI, NI, WN}
+struct GemmShape {
+    int bm, bn;
+};
+static const GemmShape GEMM_SHAPES[] = {{128, 64}, {128, 56}, {128, 48}, {64, 64}, {32, 64}};
+
+template <bool TB, bool VEC, int MI, int NI, int WN>
+static int gemm_launch(const double *A, long lda, const double *B, long ldb, double *C, long ldc, int m, int n,
+                       int k, cudaStream_t st)
+{
+    auto kern = k_gemm_f64<TB, VEC, MI, NI, WN>;
+    static bool attr = false;
+    if (!attr) {
+        PDE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        attr = true;
+    }
+    constexpr int BM = (8 / WN) * 8 * MI, BNT = WN * 8 * NI;
+    dim3 grid(ceil_div(n, BNT), ceil_div(m, BM));
+    kern<<<grid, 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, m, n, k);
+    return after_launch("pde_gemm_f64");
+}
+
+template <bool TB, bool VEC>
+static int gemm_shape(int shape, const double *A, long lda, const double *B, long ldb, double *C, long ldc, int m,
+                      int n, int k, cudaStream_t st)
+{
+    switch (shape) {
+    case 0: return gemm_launch<TB, VEC, 4, 4, 2>(A, lda, B, ldb, C, ldc, m, n, k, st);   // 128 x 64
+    case 1: return gemm_launch<TB, VEC, 2, 7, 1>(A, lda, B, ldb, C, ldc, m, n, k, st);   // 128 x 56
+    case 2: return gemm_launch<TB, VEC, 2, 6, 1>(A, lda, B, ldb, C, ldc, m, n, k, st);   // 128 x 48
+    case 3: return gemm_launch<TB, VEC, 2, 4, 2>(A, lda, B, ldb, C, ldc, m, n, k, st);   // 64 x 64
+    default: return gemm_launch<TB, VEC, 1, 4, 2>(A, lda, B, ldb, C, ldc, m, n, k, st);  // 32 x 64
+    }
+}
+
 int gemm_f64(bool transB, const double *A, long lda, const double *B, long ldb, double *C, long ldc, int m,
              int n, int k, cudaStream_t st)
 {
     if (m <= 0 || n <= 0) return PDE_OK;
     const bool vec = (lda % 2 == 0) && (ldb % 2 == 0) && (ldc % 2 == 0) &&
                      ((uintptr_t)A % 16 == 0) && ((uintptr_t)B % 16 == 0) && ((uintptr_t)C % 16 == 0);
-    // CTA tile 128 x 64 when that fills the machine, else 64 x 64 / 32 x 64 (row slabs of the
-    // multi-GPU path and small grids have few rows)
-    const int sms = sm_count();
-    int MI = 4;
-    if ((long)ceil_div(n, BN) * ceil_div(m, 128) < 2L * sms) MI = 2;
-    if ((long)ceil_div(n, BN) * ceil_div(m, 64) < 2L * sms) MI = 1;
-    dim3 grid(ceil_div(n, BN), ceil_div(m, 32 * MI));
-    static bool attr = false;
-    auto set_attr = [&](auto kern) {
-        return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
-    };
-    if (!attr) {
-#define PDE_GEMM_ATTR(TBV, VECV)                                  \
-        PDE_CUDA(set_attr(k_gemm_f64<TBV, VECV, 4>));               \
-        PDE_CUDA(set_attr(k_gemm_f64<TBV, VECV, 2>));               \
-        PDE_CUDA(set_attr(k_gemm_f64<TBV, VECV, 1>));
-        PDE_GEMM_ATTR(false, false)
-        PDE_GEMM_ATTR(false, true)
-        PDE_GEMM_ATTR(true, false)
-        PDE_GEMM_ATTR(true, true)
-#undef PDE_GEMM_ATTR
-        attr = true;
-    }
-#define PDE_GEMM_LAUNCH(TBV, VECV)                                                                              \
-    do {                                                                                                        \
-        if (MI == 4) k_gemm_f64<TBV, VECV, 4><<<grid, 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, m, n, k);   \
-        else if (MI == 2) k_gemm_f64<TBV, VECV, 2><<<grid, 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, m, n, k); \
-        else k_gemm_f64<TBV, VECV, 1><<<grid, 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, m, n, k);           \
-    } while (0)
-    if (transB) {
-        if (vec) PDE_GEMM_LAUNCH(true, true);
-        else PDE_GEMM_LAUNCH(true, false);
+    // Tile shape: the one that needs the least (waves x tile area) with 2 CTAs per SM; 64- and 32-row
+    // tiles only when the 128-row ones cannot fill the machine (row slabs of the multi-GPU path, small grids).
+    const long slots = 2L * sm_count();
+    int shape = 0;
+    static const int forced = getenv("PDE_GEMM_SHAPE") ? atoi(getenv("PDE_GEMM_SHAPE")) : -1;
+    if (forced >= 0 && forced <= 4) {
+        shape = forced;
+    } else if ((long)ceil_div(n, 64) * ceil_div(m, 64) < slots) {
+        shape = 4;
+    } else if ((long)ceil_div(n, 64) * ceil_div(m, 128) < slots) {
+        shape = 3;
     } else {
-        if (vec) PDE_GEMM_LAUNCH(false, true);
-        else PDE_GEMM_LAUNCH(false, false);
+        double best = 0.0;
+        for (int sidx = 0; sidx < 3; ++sidx) {
+            const GemmShape &g = GEMM_SHAPES[sidx];
+            const long tiles = (long)ceil_div(n, g.bn) * ceil_div(m, g.bm);
+            // narrower tiles re-read A more often and issue more fragment loads per DMMA: 3 % handicap per step
+            const double cost = (double)ceil_div(tiles, slots) * g.bm * g.bn * (1.0 + 0.03 * sidx);
+            if (sidx == 0 || cost < best) {
+                best = cost;
+                shape = sidx;
+            }
+        }
     }
-#undef PDE_GEMM_LAUNCH
-    return after_launch("pde_gemm_f64");
+    if (transB) return vec ? gemm_shape<true, true>(shape, A, lda, B, ldb, C, ldc, m, n, k, st)
+                           : gemm_shape<true, false>(shape, A, lda, B, ldb, C, ldc, m, n, k, st);
+    return vec ? gemm_shape<false, true>(shape, A, lda, B, ldb, C, ldc, m, n, k, st)
+               : gemm_shape<false, false>(shape, A, lda, B, ldb, C, ldc, m, n, k, st);
 }
 
 }  // namespace pde

@@ -78,12 +78,26 @@ template <bool LC>
 struct Writer {
     double *p0;        // element 0 of this thread's sequence
     unsigned ld;       // row pitch (LC: element stride of the sequence)
+    double *pc;        // TS, interior chunks: element `ibase` (set once per chunk)
+    int ibase;
     __device__ __forceinline__ Writer(double *base, long ld_, int q)
-        : p0(LC ? base + q : base + (long)q * ld_), ld((unsigned)ld_) {}
+        : p0(LC ? base + q : base + (long)q * ld_), ld((unsigned)ld_), pc(p0), ibase(0) {}
+    __device__ __forceinline__ void chunk(int i0)
+    {
+        if (!LC) {
+            ibase = i0;
+            pc = p0 + (unsigned)i0;
+        }
+    }
+    // MID = interior chunk.  TS: i - ibase folds to a compile-time constant after inlining, so the store is
+    // STG [pc + imm] (the plain p0[i] form spent 4 integer instructions per store on the sign-extended
+    // 64-bit address: SASS of the first version).  LC: unsigned 32 x 32 -> 64 is ONE instruction
+    // (IMAD.WIDE.U32); the signed / 64-bit forms cost 4-6.
+    template <bool MID = false>
     __device__ __forceinline__ void st(int i, double v) const
     {
-        // unsigned 32 x 32 -> 64 is ONE instruction (IMAD.WIDE.U32); the signed / 64-bit forms cost 4-6
         if (LC) p0[(unsigned long long)(unsigned)i * ld] = v;
+        else if (MID) pc[i - ibase] = v;
         else p0[i] = v;
     }
 };
@@ -227,6 +241,7 @@ __global__ void __launch_bounds__(BD) k_sweep(SweepJobs jobs)
         else if (c + SW_KC - 1 < nchunks) issue_chunk(c + SW_KC - 1);
         cp_async_commit_group();
         const int i0 = Op::ASC ? par + 2 * c * C : top - 2 * c * C;
+        out.chunk(i0);
 #pragma unroll
         for (int e = 0; e < C; ++e) Op::template step<true>(st, job, n, Op::ASC ? i0 + 2 * e : i0 - 2 * e, v[e], out);
     };
@@ -261,7 +276,9 @@ __global__ void __launch_bounds__(BD) k_sweep(SweepJobs jobs)
 
 // differentiate_cheby.f90:28-53: dc[n-1] = 0, dc[n-2] = 2(n-1)c[n-1], dc[k] = dc[k+2] + 2(k+1)c[k+1],
 // dc[0] = dc[2]/2 + c[1]; stored value divided by job.sc when job.flag (grad(): /= scale**deriv).
-template <bool FULL>
+// POW2: every job's scale is a power of two (aspect 1: scale = 1/2), so x / sc == x * RN(1/sc) bit for bit
+// and the 5-op division sequence becomes one multiplication.
+template <bool FULL, bool POW2 = false>
 struct DiffDesc {
     static constexpr int NIN = 1;
     static constexpr int NT = 0;
@@ -292,14 +309,15 @@ struct DiffDesc {
         if (MID) {
             cur = s.p + (double)(2 * i) * v[0];
         } else {
-            if (i == n - 1) out.st(n - 1, 0.0);
+            if (i == n - 1) out.template st<false>(n - 1, 0.0);
             if (i == 0) return;
             if (i == n - 1) cur = (double)(2 * (n - 1)) * v[0];
             else if (k >= 1) cur = s.p + (double)(2 * i) * v[0];
             else cur = s.p / 2.0 + v[0];
         }
         s.p = cur;
-        out.st(k, s.div ? div_rn_v(cur, s.sc, s.rsc, true) : cur);
+        if (POW2) out.template st<MID>(k, cur * s.rsc);
+        else out.template st<MID>(k, s.div ? div_rn_v(cur, s.sc, s.rsc, true) : cur);
     }
 };
 
@@ -341,7 +359,7 @@ struct TdmaFwd {
         if (!MID && i < 2) g = rhs / den;
         else g = div_rn_v(rhs - PDE_TB(s, 1, i - 2) * s.g, den, PDE_TB(s, 3, i), s.has_r);
         s.g = g;
-        out.st(i, g);
+        out.template st<MID>(i, g);
     }
 };
 
@@ -367,7 +385,7 @@ struct TdmaBwd {
         double x = v[0];
         if (MID || i < n - 2) {
             x = v[0] - PDE_TB(s, 0, i) * s.x;
-            out.st(i, x);
+            out.template st<MID>(i, x);
         }
         s.x = x;
     }
@@ -395,7 +413,7 @@ struct FdmaFwd {
         double x = v[0];
         if (MID || i >= 2) {
             x = v[0] - PDE_TB(s, 0, i - 2) * s.p;
-            out.st(i, x);
+            out.template st<MID>(i, x);
         }
         s.p = x;
     }
@@ -429,7 +447,7 @@ struct FdmaBwd {
         if (!MID && i >= n - 2) x = v[0] / d;
         else if (!MID && i >= n - 4) x = (v[0] - PDE_TB(s, 1, i) * s.x2) / d;
         else x = div_rn_v(v[0] - PDE_TB(s, 1, i) * s.x2 - PDE_TB(s, 2, i) * s.x4, d, PDE_TB(s, 3, i), s.has_r);
-        out.st(i, x);
+        out.template st<MID>(i, x);
         s.x4 = s.x2;
         s.x2 = x;
     }
@@ -463,7 +481,7 @@ struct TwodmaBwd {
         double x;
         if (!MID && i >= n - 2) x = v[0] / d;
         else x = div_rn_v(v[0] - PDE_TB(s, 1, i) * s.x, d, PDE_TB(s, 2, i), s.has_r);
-        out.st(i, x);
+        out.template st<MID>(i, x);
         s.x = x;
     }
 };
@@ -495,13 +513,13 @@ struct PoissonFwd {
     __device__ static void step(State &s, const SweepJob &, int, int i, const double *v, W &out)
     {
         if (!MID && i < s.off) {
-            out.st(i, 0.0);
+            out.template st<MID>(i, 0.0);
             return;
         }
         double x = v[0];
         if (MID || i >= s.off + 2) {
             x = v[0] - v[1] * s.p;
-            out.st(i, x);
+            out.template st<MID>(i, x);
         }
         s.p = x;
     }
@@ -536,7 +554,7 @@ struct PoissonBwd {
         if (!MID && i >= n - 2) x = v[0] / v[1];
         else if (!MID && i >= n - 4) x = (v[0] - v[2] * s.x2) / v[1];
         else x = div_rn_v(v[0] - v[2] * s.x2 - v[3] * s.x4, v[1], v[4], true);
-        out.st(i, x);
+        out.template st<MID>(i, x);
         s.x4 = s.x2;
         s.x2 = x;
     }

@@ -240,10 +240,12 @@ class FastStepper:
 
         # -- spectral pre-processing: Chebyshev coefficients of u, w and of all first derivatives
         self._stencil(calls, 0, [(self.sx["U"], U, cU), (self.sx["V"], V, cV), (self.sx["T"], T, cT)])
-        self._diff(calls, 0, [(cU, dU), (cV, dV), (cT, dT)], sx)
+        # (the pressure gradient of the right-hand sides only needs stage-start data: its two single-array
+        # recurrences ride along with the batched ones instead of occupying one warp per SM on their own)
+        self._diff(calls, 0, [(cU, dU), (cV, dV), (cT, dT), (pres, self.dpdx)], sx)
         self._stencil(calls, 1, [(self.sy["U"], cU, eU), (self.sy["V"], cV, eV), (self.sy["T"], cT, eT),
                                  (self.sy["U"], dU, fU), (self.sy["V"], dV, fV), (self.sy["T"], dT, fT)])
-        self._diff(calls, 1, [(eU, gU), (eV, gV), (eT, gT)], sz)
+        self._diff(calls, 1, [(eU, gU), (eV, gV), (eT, gT), (pres, self.dpdz)], sz)
         self._lincomb(calls, [(self.thc, [(1.0, eT), (1.0, self.tbc_cheby)])])      # That (buoyancy)
         # -- 8 backward 2-D transforms onto the (dealiased) grid
         src = [eU, eV, fU, fV, fT, gU, gV, gT]
@@ -259,8 +261,6 @@ class FastStepper:
         self._dct(calls, self.plan1, ops.FWD, 1, [dxU, dxV, dxT], [f[:, : self.N1] for f in self.F3])
         self._dct(calls, self.plan0, ops.FWD, 0, [f[:, : self.N1] for f in self.F3], [cv[: self.N0] for cv in self.conv])
         # -- right-hand sides (Chebyshev space)
-        self._diff(calls, 0, [(pres, self.dpdx)], sx)
-        self._diff(calls, 1, [(pres, self.dpdz)], sz)
         rU, rV, rT = self.rhs
         self._lincomb(calls, [
             (rU, [(-dt * a, self.dpdx), (-dt, self.conv[0])]),

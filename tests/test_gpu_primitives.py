@@ -147,7 +147,11 @@ def test_banded_product_and_dense_product(dev):
         assert rel_l2(H(PlanRHS(D, ndim=2, axis=axis).solve(T(b, dev))), ref) < 1e-14
 
 
-@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (7, 5, 3), (128, 64, 16), (129, 65, 17), (300, 257, 511), (62, 62, 64)])
+# the last five sizes select, on 148 SMs, the 128x56, 128x48, 128x64, 64x64 tile shapes and the unaligned
+# (scalar cp.async) path of the 128x56 one (pde::gemm_f64 picks the shape that fills whole waves)
+@pytest.mark.parametrize("m,n,k", [(1, 1, 1), (7, 5, 3), (128, 64, 16), (129, 65, 17), (300, 257, 511), (62, 62, 64),
+                                   (1874, 1874, 33), (1538, 1538, 40), (2050, 2050, 20), (1090, 1090, 24),
+                                   (1875, 1877, 9)])
 @pytest.mark.parametrize("transB", [False, True])
 def test_gemm_f64(dev, m, n, k, transB):
     import torch
@@ -345,3 +349,34 @@ def test_auto_algo_selection(dev):
     assert ops.DctPlan(3073).algo == 2
     assert ops.DctPlan(2048).algo == 3        # L-1 = 2047 = 23 * 89: Bluestein
     assert ops.DctPlan(6144).algo == 1        # L-1 = 6143 prime, M = 16384 does not fit: dense fallback
+
+
+@pytest.mark.parametrize("axis", [0, 1])
+@pytest.mark.parametrize("scales", [(0.5, 0.5, 0.5), (0.25, 2.0, 1.0), (0.5, 0.75, 1.0)])
+def test_batched_diff_sweep_bit_exact(dev, axis, scales):
+    """pde_sweep(DIFF) with several jobs of different widths in one launch (the stepper's batched form).
+    Power-of-two scales take the multiply-by-reciprocal instantiation (x / 2^k == x * 2^-k), any other
+    scale the correctly rounded division sequence: both must equal diff_2d(c) / scale bit for bit
+    (differentiate_cheby.f90:28-53, field_operations.py:40-45)."""
+    import torch
+    from pypde_b200 import _cabi as C
+    from oracle import kernels as K
+    rng = np.random.default_rng(5 + axis)
+    n = 203                                  # several interior chunks + ragged edges
+    widths = (70, 33, 1)
+    arr = (C.SweepJob * len(widths))()
+    keep, refs = [], []
+    for k, (w, sc) in enumerate(zip(widths, scales)):
+        c = rng.standard_normal((n, w) if axis == 0 else (w, n))
+        ref = K.diff_2d(c if axis == 0 else np.ascontiguousarray(c.T))
+        ref = ref if axis == 0 else ref.T
+        refs.append(ref / sc if sc != 1.0 else ref)
+        x, y = T(c, dev), torch.full(c.shape, np.nan, dtype=torch.float64, device=dev)
+        keep += [x, y]
+        j = arr[k]
+        j.inp[0], j.ldin[0], j.out, j.ldout = x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0)
+        j.nseq, j.flag, j.sc = w, int(sc != 1.0), sc
+    C.check(C.lib().pde_sweep(0, axis, n, len(widths), arr, C.stream()))
+    torch.cuda.synchronize()
+    for k, ref in enumerate(refs):
+        assert np.array_equal(H(keep[2 * k + 1]), ref), "job %d" % k
