@@ -143,6 +143,35 @@ __device__ __forceinline__ void dif_pass_t(double2 *z, const double2 *__restrict
     constexpr int R1 = P / M1;                             // first radix = number of first-level blocks
     constexpr int NBLK = P / NCUR;                         // blocks of this level per sequence
     static_assert(NCUR == P || NBLK % R1 == 0, "levels nest inside the first-level blocks");
+#ifdef PDE_FFT_NO_TW_REUSE
+    constexpr bool TW_REUSE = false;
+#else
+    constexpr bool TW_REUSE = true;
+#endif
+    // First pass of a CTA that holds several sequences (axis 0): butterfly j of every sequence uses the same
+    // R - 1 twiddles, and the [r][j] table of this pass is the large one (15 x 192 x 16 B = 46 KB, 4 L1 lines per
+    // warp request).  ncu (r01_ncu_dct_fft_remap.csv): 0.6 M of the kernel's 1.0 M global load requests were
+    // twiddles, ~17 % of the L1TEX cycles.  Keep them in registers across the thread's sequences.
+    if constexpr (TW_REUSE && NCUR == P && S > 1 && WOFF >= 0 && M > 1 && T % PER_SEQ == 0 &&
+                  S % (T / PER_SEQ) == 0) {
+        constexpr int SPT = T / PER_SEQ;                   // sequences per sweep of the CTA
+        const int j = (int)threadIdx.x % PER_SEQ, s0 = (int)threadIdx.x / PER_SEQ;
+        double2 w[R - 1];
+#pragma unroll
+        for (int r = 1; r < R; ++r) w[r - 1] = __ldg(W + WOFF + (r - 1) * M + j);
+#pragma unroll
+        for (int sq = 0; sq < S / SPT; ++sq) {
+            double2 *p = z + (s0 + sq * SPT) * PS + j;
+            double2 a[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) a[r] = p[r * RS];
+            dft<R>(a);
+#pragma unroll
+            for (int r = 1; r < R; ++r) a[r] = cmul(a[r], w[r - 1]);
+#pragma unroll
+            for (int r = 0; r < R; ++r) p[r * RS] = a[r];
+        }
+    } else {
 #pragma unroll
     for (int b0 = 0; b0 < TOTAL; b0 += T) {
         const int b = b0 + threadIdx.x;
@@ -171,6 +200,7 @@ __device__ __forceinline__ void dif_pass_t(double2 *z, const double2 *__restrict
         }
 #pragma unroll
         for (int r = 0; r < R; ++r) p[r * RS] = a[r];
+    }
     }
 }
 

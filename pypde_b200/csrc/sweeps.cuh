@@ -30,6 +30,14 @@ static_assert(true, "");
 #endif
 constexpr int SW_KC = PDE_SW_KC;         // chunks in the ring (SW_KC-1 chunks = 24 steps in flight per thread)
 constexpr int RING_K = SW_C * SW_KC;
+// TS sweeps: every lane streams through its own row with 8-byte copies, so DRAM sees isolated 32-byte
+// sectors of 32 different rows per warp step.  Each lane therefore asks L2 for the 128-byte window of a
+// chunk SW_PF chunks ahead of its cp.async ring (one cp.async.bulk.prefetch.L2 per chunk and stream):
+// DRAM is read in whole-line requests and the ring's copies hit L2.  0 = off.
+#ifndef PDE_SW_PF
+#define PDE_SW_PF 0
+#endif
+constexpr int SW_PF = PDE_SW_PF;
 constexpr int SWEEP_MAX_JOBS = 8;
 constexpr int SWEEP_MAX_IN = 5;
 
@@ -47,6 +55,10 @@ __device__ __forceinline__ void cp_async_8(double *smem, const double *gmem)
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2_128(const double *gmem)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], 128;\n" ::"l"(gmem) : "memory");
+}
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
@@ -138,6 +150,20 @@ __global__ void __launch_bounds__(BD) k_sweep(SweepJobs jobs)
         slen[s] = job.in[s] ? Op::len(s, n, job) : 0;
     }
     Writer<LC> out(job.out, job.ldout, q);
+    // L2 prefetch (TS only): rows must start on 16-byte boundaries
+    bool pf_ok[NIN];
+#pragma unroll
+    for (int s = 0; s < NIN; ++s)
+        pf_ok[s] = !LC && SW_PF > 0 && gq[s] != nullptr && ((unsigned long long)job.in[s] % 16 == 0) &&
+                   (job.ldin[s] % 2 == 0);
+    auto prefetch_chunk = [&](int c) {
+        if (LC || SW_PF == 0) return;
+        // elements [w0, w0 + 16) hold both parity chains' steps of chunk c (w0 even => 16-byte aligned)
+        const int w0 = Op::ASC ? 2 * c * C : ((top - 2 * c * C - 2 * (C - 1)) & ~1);
+#pragma unroll
+        for (int s = 0; s < NIN; ++s)
+            if (pf_ok[s] && w0 >= 0 && w0 + 2 * C <= slen[s]) prefetch_l2_128(gq[s] + w0);
+    };
 
     // generic (checked) chunk issue: steps c*C .. c*C+C-1 into ring chunk slot c % KC
     auto issue_chunk = [&](int c) {
@@ -240,6 +266,7 @@ __global__ void __launch_bounds__(BD) k_sweep(SweepJobs jobs)
         if (c + SW_KC - 1 < c_hi) issue_fast(c + SW_KC - 1, std::integral_constant<int, NS>{});
         else if (c + SW_KC - 1 < nchunks) issue_chunk(c + SW_KC - 1);
         cp_async_commit_group();
+        prefetch_chunk(c + SW_KC - 1 + SW_PF);
         const int i0 = Op::ASC ? par + 2 * c * C : top - 2 * c * C;
         out.chunk(i0);
 #pragma unroll
