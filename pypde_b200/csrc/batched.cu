@@ -4,6 +4,8 @@
 // NumPy / SciPy expressions of the reference.
 #include "common.cuh"
 #include <cmath>
+#include <cstdint>
+#include <cstdlib>
 #include "sweeps.cuh"
 
 namespace pde {
@@ -91,6 +93,118 @@ __global__ void __launch_bounds__(256, 4) k_banded_multi(BandJobs jobs, int axis
             if (ok[r][d] && a[r][d] != 0.0) acc = acc + a[r][d] * xv[r][d];
         jb.y[(long)i * jb.ldy + j] = jb.accumulate ? yo[r] + acc : acc;
     }
+}
+
+// Strip form of the banded product for the stepper's operators (diagonals at off0, off0 + 2, ..., at most 4,
+// even sizes and pitches, 16-byte aligned rows): a thread owns TWO adjacent columns (16-byte accesses) and a
+// strip of rows, so every operand element is loaded once per thread instead of once per tap.
+//   axis 0 (taps along the rows): a register window of RS0 + 6 input rows feeds RS0 output rows
+//           (1.75 loads per 2 outputs instead of 8); the coefficients of the strip are warp-uniform 16-byte loads;
+//   axis 1 (taps along the contiguous axis): the coefficients of the two columns are loaded once per thread and
+//           reused over RS1 rows; the taps of a row are nd aligned 16-byte loads.
+// Same products, same order of sums, zero coefficients skipped: bit-identical to k_banded_multi.
+constexpr int RS0 = 4, RS1 = 4;
+
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
+
+template <int AXIS>
+__global__ void __launch_bounds__(256, 2) k_banded_strip(BandJobs jobs)
+{
+    const pde_band_job &jb = jobs.j[blockIdx.z];
+    const int n0 = AXIS == 0 ? jb.n_out : jb.batch, n1 = AXIS == 0 ? jb.batch : jb.n_out;
+    const int jp = 2 * (blockIdx.x * blockDim.x + threadIdx.x);
+    if (jp >= n1) return;
+    const int nd = jb.ndiag, o0 = jb.off[0];
+    if (AXIS == 0) {
+        const int i0 = (blockIdx.y * blockDim.y + threadIdx.y) * RS0;
+        if (i0 >= n0) return;
+        constexpr int W = RS0 + 6;
+        double2 xw[W], yo[RS0];
+        double a[4][RS0];
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const int c = i0 + o0 + w;
+            xw[w] = (w < RS0 + 2 * (nd - 1) && c >= 0 && c < jb.n_in) ? ld2(jb.x + (long)c * jb.ldx + jp)
+                                                                      : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+#pragma unroll
+            for (int r = 0; r < RS0; r += 2) {
+                // rows i0 + r, i0 + r + 1 of diagonal d (n_out even, i0 a multiple of RS0: aligned, in range together)
+                const double2 t = (d < nd && i0 + r < n0) ? ldg2(jb.diags + (long)d * jb.n_out + i0 + r)
+                                                          : make_double2(0.0, 0.0);
+                a[d][r] = t.x;
+                a[d][r + 1] = t.y;
+            }
+        if (jb.accumulate) {
+#pragma unroll
+            for (int r = 0; r < RS0; ++r)
+                yo[r] = i0 + r < n0 ? ld2(jb.y + (long)(i0 + r) * jb.ldy + jp) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int r = 0; r < RS0; ++r) {
+            const int i = i0 + r;
+            if (i >= n0) break;
+            double ax = 0.0, ay = 0.0;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                const int c = i + o0 + 2 * d;
+                if (d < nd && c >= 0 && c < jb.n_in && a[d][r] != 0.0) {
+                    ax = ax + a[d][r] * xw[r + 2 * d].x;
+                    ay = ay + a[d][r] * xw[r + 2 * d].y;
+                }
+            }
+            double2 *yp = reinterpret_cast<double2 *>(jb.y + (long)i * jb.ldy + jp);
+            *yp = jb.accumulate ? make_double2(yo[r].x + ax, yo[r].y + ay) : make_double2(ax, ay);
+        }
+    } else {
+        const int i0 = (blockIdx.y * blockDim.y + threadIdx.y) * RS1;
+        if (i0 >= n0) return;
+        double2 a[4], xd[RS1][4], yo[RS1];
+        bool ok[4];
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const int c = jp + o0 + 2 * d;
+            ok[d] = d < nd && c >= 0 && c < jb.n_in;
+            a[d] = ok[d] ? ldg2(jb.diags + (long)d * jb.n_out + jp) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int r = 0; r < RS1; ++r) {
+            const int i = i0 + r;
+#pragma unroll
+            for (int d = 0; d < 4; ++d)
+                xd[r][d] = (ok[d] && i < n0) ? ld2(jb.x + (long)i * jb.ldx + jp + o0 + 2 * d) : make_double2(0.0, 0.0);
+            if (jb.accumulate) yo[r] = i < n0 ? ld2(jb.y + (long)i * jb.ldy + jp) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int r = 0; r < RS1; ++r) {
+            const int i = i0 + r;
+            if (i >= n0) break;
+            double ax = 0.0, ay = 0.0;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                if (ok[d] && a[d].x != 0.0) ax = ax + a[d].x * xd[r][d].x;
+                if (ok[d] && a[d].y != 0.0) ay = ay + a[d].y * xd[r][d].y;
+            }
+            double2 *yp = reinterpret_cast<double2 *>(jb.y + (long)i * jb.ldy + jp);
+            *yp = jb.accumulate ? make_double2(yo[r].x + ax, yo[r].y + ay) : make_double2(ax, ay);
+        }
+    }
+}
+
+static bool band_strip_ok(const pde_band_job &jb, int axis)
+{
+    if (jb.ndiag < 1 || jb.ndiag > 4) return false;
+    for (int d = 1; d < jb.ndiag; ++d)
+        if (jb.off[d] != jb.off[0] + 2 * d) return false;
+    if (jb.off[0] % 2 != 0 || jb.off[0] < -2 || jb.off[0] > 0) return false;
+    auto al = [](const void *q) { return ((uintptr_t)q % 16) == 0; };
+    if (!al(jb.x) || !al(jb.y) || !al(jb.diags) || jb.ldx % 2 || jb.ldy % 2) return false;
+    if (jb.n_out % 2 || jb.n_in % 2 || jb.batch % 2) return false;
+    (void)axis;
+    return true;
 }
 
 struct LincombJobs {
@@ -184,6 +298,12 @@ __global__ void k_slab_repack(int dir, double *__restrict__ bundle, double *__re
 
 using namespace pde;
 
+namespace pde {
+// DiffDesc with the power-of-two scale, in the <FULL, TAB> shape the tiled launcher expects
+template <bool FULL, class TAB>
+using DiffPow2 = DiffDesc<FULL, true, TAB>;
+}  // namespace pde
+
 extern "C" {
 
 int pde_sweep(int op, int axis, int n, int njobs, const pde_sweep_job *jobs, void *stream)
@@ -214,22 +334,36 @@ int pde_sweep(int op, int axis, int n, int njobs, const pde_sweep_job *jobs, voi
         default: break;
         }
     }
+    // axis 1: tiled kernel (k_sweep_tile) when sizes / alignment allow; PDE_SWEEP_TILE=0 keeps k_sweep
+    static const bool tile = !(getenv("PDE_SWEEP_TILE") && atoi(getenv("PDE_SWEEP_TILE")) == 0);
+#define PDE_TILE(OPT, FULLV, what)                                                           \
+    if (tile && axis == 1 && sweep_tile_ok<OPT<FULLV, TabTile>>(sj)) return launch_sweep_tile<OPT, FULLV>(sj, st, what)
 #define PDE_SW(OP, what) (full ? launch_sweep<OP<true>>(sj, axis, st, what) : launch_sweep<OP<false>>(sj, axis, st, what))
     switch (op) {
     case PDE_SWEEP_DIFF:
         if (pow2) {
             for (int j = 0; j < njobs; ++j)
                 if (sj.j[j].flag == 0) sj.j[j].sc = 1.0;
+            PDE_TILE(DiffPow2, true, "pde_sweep(diff, pow2 scale, tiled)");
             return launch_sweep<DiffDesc<true, true>>(sj, axis, st, "pde_sweep(diff, pow2 scale)");
         }
         return PDE_SW(DiffDesc, "pde_sweep(diff)");
-    case PDE_SWEEP_TDMA_FWD: return PDE_SW(TdmaFwd, "pde_sweep(tdma fwd)");
-    case PDE_SWEEP_TDMA_BWD: return launch_sweep<TdmaBwd<true>>(sj, axis, st, "pde_sweep(tdma bwd)");
-    case PDE_SWEEP_FDMA_FWD: return launch_sweep<FdmaFwd<true>>(sj, axis, st, "pde_sweep(fdma fwd)");
-    case PDE_SWEEP_FDMA_BWD: return PDE_SW(FdmaBwd, "pde_sweep(fdma bwd)");
+    case PDE_SWEEP_TDMA_FWD:
+        if (full) PDE_TILE(TdmaFwd, true, "pde_sweep(tdma fwd, tiled)");
+        return PDE_SW(TdmaFwd, "pde_sweep(tdma fwd)");
+    case PDE_SWEEP_TDMA_BWD:
+        PDE_TILE(TdmaBwd, true, "pde_sweep(tdma bwd, tiled)");
+        return launch_sweep<TdmaBwd<true>>(sj, axis, st, "pde_sweep(tdma bwd)");
+    case PDE_SWEEP_FDMA_FWD:
+        PDE_TILE(FdmaFwd, true, "pde_sweep(fdma fwd, tiled)");
+        return launch_sweep<FdmaFwd<true>>(sj, axis, st, "pde_sweep(fdma fwd)");
+    case PDE_SWEEP_FDMA_BWD:
+        if (full) PDE_TILE(FdmaBwd, true, "pde_sweep(fdma bwd, tiled)");
+        return PDE_SW(FdmaBwd, "pde_sweep(fdma bwd)");
     case PDE_SWEEP_TWODMA_BWD: return launch_sweep<TwodmaBwd<false>>(sj, axis, st, "pde_sweep(twodma)");
     default: set_error("pde_sweep: unknown op %d", op); return PDE_ERR_ARG;
     }
+#undef PDE_TILE
 #undef PDE_SW
 }
 
@@ -268,6 +402,15 @@ int pde_banded_multi(int axis, int njobs, const pde_band_job *jobs, void *stream
         m1 = n1 > m1 ? n1 : m1;
     }
     if (m0 <= 0 || m1 <= 0) return PDE_OK;
+    static const bool strip = !(getenv("PDE_BANDED_STRIP") && atoi(getenv("PDE_BANDED_STRIP")) == 0);
+    bool strip_ok = strip;
+    for (int j = 0; j < njobs && strip_ok; ++j) strip_ok = band_strip_ok(jobs[j], axis);
+    if (strip_ok) {
+        dim3 block(64, 4), grid(ceil_div(m1, 128), ceil_div(m0, 4 * (axis == 0 ? RS0 : RS1)), njobs);
+        if (axis == 0) k_banded_strip<0><<<grid, block, 0, as_stream(stream)>>>(bj);
+        else k_banded_strip<1><<<grid, block, 0, as_stream(stream)>>>(bj);
+        return after_launch("pde_banded_multi(strip)");
+    }
     dim3 block(64, 4), grid(ceil_div(m1, 64), ceil_div(m0, 4 * RPB), njobs);
     if (maxd <= 4) k_banded_multi<4><<<grid, block, 0, as_stream(stream)>>>(bj, axis);
     else k_banded_multi<8><<<grid, block, 0, as_stream(stream)>>>(bj, axis);

@@ -20,6 +20,7 @@
 #pragma once
 #include "common.cuh"
 #include <type_traits>
+#include <cstdint>
 
 namespace pde {
 
@@ -116,7 +117,7 @@ struct Writer {
 
 // Op interface:
 //   static constexpr int NIN;  static constexpr bool ASC;
-//   __device__ static int off(int s);                 index offset of stream s
+//   __host__ __device__ static int off(int s);                 index offset of stream s
 //   __device__ static int len(int s, int n, job);     valid index range [0, len) of stream s
 //   struct State;  __device__ static void init(State&, job, n, q);
 //   template <class W> __device__ static void step(State&, job, n, i, const double *v, W &out);
@@ -299,24 +300,44 @@ __global__ void __launch_bounds__(BD) k_sweep(SweepJobs jobs)
 // generic C-ABI entry points use FULL = false.  A thread walks ONE parity chain, so the
 // recurrence state is a single value.  Per-index tables are read from the shared-memory copy
 // staged by k_sweep: table k, index i  ->  tsm[k*H + (i >> 1)]  (i has the chain's parity).
-#define PDE_TB(st, k, i) ((st).tsm[(k) * (st).H + ((i) >> 1)])
+#define PDE_TB(st, k, i) ((st).tb((k), (i)))
+
+// Where an operator finds its per-index tables:
+//   TabParity (k_sweep):      the parity half this thread walks, staged per CTA: table k, index i -> tsm[k*H + (i >> 1)]
+//   TabTile   (k_sweep_tile): the slice [i0 - 2, i0 + TW + 2) of every table, staged per tile:  tt[k*TTP + (i - i0) + 2]
+struct TabParity {
+    const double *tsm;
+    int H;
+    __device__ __forceinline__ double tb(int k, int i) const { return tsm[k * H + (i >> 1)]; }
+};
+constexpr int TILE_W = 64;               // elements of a sequence per tile
+constexpr int TILE_P = TILE_W + 2;       // row pitch of a tile in shared memory (33 x 16 bytes: odd, conflict-free)
+constexpr int TILE_TP = TILE_W + 4;      // table slice per tile
+struct TabTile {
+    const double *tt;
+    int i0;
+    __device__ __forceinline__ double tb(int k, int i) const { return tt[k * TILE_TP + (i - i0) + 2]; }
+};
 
 // differentiate_cheby.f90:28-53: dc[n-1] = 0, dc[n-2] = 2(n-1)c[n-1], dc[k] = dc[k+2] + 2(k+1)c[k+1],
 // dc[0] = dc[2]/2 + c[1]; stored value divided by job.sc when job.flag (grad(): /= scale**deriv).
 // POW2: every job's scale is a power of two (aspect 1: scale = 1/2), so x / sc == x * RN(1/sc) bit for bit
 // and the 5-op division sequence becomes one multiplication.
-template <bool FULL, bool POW2 = false>
+template <bool FULL, bool POW2 = false, class TAB = TabParity>
 struct DiffDesc {
     static constexpr int NIN = 1;
     static constexpr int NT = 0;
     static constexpr bool ASC = false;
-    __device__ static int off(int) { return 0; }
+    // k_sweep_tile: step index of output k is k + ISHIFT; HALO: reads input element i + 2 (or k + 1);
+    // PARTIAL: some indices are not stored (in place only: the tile is pre-filled with the input)
+    static constexpr int ISHIFT = 1;
+    static constexpr bool HALO = true;
+    static constexpr bool PARTIAL = false;
+    __host__ __device__ static int off(int) { return 0; }
     __device__ static int len(int, int n, const SweepJob &) { return n; }
-    __device__ static int tab_index(int) { return 0; }
-    __device__ static int tab_len(int, int) { return 0; }
-    struct State {
-        const double *tsm;
-        int H;
+    __host__ __device__ static int tab_index(int) { return 0; }
+    __host__ __device__ static int tab_len(int, int) { return 0; }
+    struct State : TAB {
         double p;          // dc[k+2] of this chain
         double sc, rsc;    // scale and RN(1/scale): the division is a 5-op correctly rounded sequence
         bool div;
@@ -351,22 +372,25 @@ struct DiffDesc {
 // tdma.f90:55-106, k = 2, forward part: g_i = (rhs_i - a_{i-2} g_{i-2}) / den_i with the fused
 // S^T product rhs_i = u_i + s_i u_{i+2} (chebyshev.py:327) when tab[0] = s is given.
 // job.tab: 0 = s (or null), 1 = a, 2 = den, 3 = w (back substitution), 4 = RN(1/den) (optional).
-template <bool FULL>
+template <bool FULL, class TAB = TabParity>
 struct TdmaFwd {
     static constexpr int NIN = 2;
     static constexpr int NT = 4;          // staged: 0 = s, 1 = a, 2 = den, 3 = rden
     static constexpr bool ASC = true;
-    __device__ static int off(int s) { return s == 0 ? 0 : 2; }
+    // k_sweep_tile: step index of output k is k + ISHIFT; HALO: reads input element i + 2 (or k + 1);
+    // PARTIAL: some indices are not stored (in place only: the tile is pre-filled with the input)
+    static constexpr int ISHIFT = 0;
+    static constexpr bool HALO = true;
+    static constexpr bool PARTIAL = false;
+    __host__ __device__ static int off(int s) { return s == 0 ? 0 : 2; }
     __device__ static int len(int s, int n, const SweepJob &job)
     {
         if (s == 0) return n;
         return job.tab[0] ? n + 2 : 0;
     }
-    __device__ static int tab_index(int k) { return k == 3 ? 4 : k; }
-    __device__ static int tab_len(int k, int n) { return k == 1 ? n - 2 : n; }
-    struct State {
-        const double *tsm;
-        int H;
+    __host__ __device__ static int tab_index(int k) { return k == 3 ? 4 : k; }
+    __host__ __device__ static int tab_len(int k, int n) { return k == 1 ? n - 2 : n; }
+    struct State : TAB {
         double g;
         bool has_s, has_r;
     };
@@ -391,18 +415,21 @@ struct TdmaFwd {
 };
 
 // back substitution x_i = g_i - w_i x_{i+2} (in place), job.tab[3] = w
-template <bool FULL>
+template <bool FULL, class TAB = TabParity>
 struct TdmaBwd {
     static constexpr int NIN = 1;
     static constexpr int NT = 1;
     static constexpr bool ASC = false;
-    __device__ static int off(int) { return 0; }
+    // k_sweep_tile: step index of output k is k + ISHIFT; HALO: reads input element i + 2 (or k + 1);
+    // PARTIAL: some indices are not stored (in place only: the tile is pre-filled with the input)
+    static constexpr int ISHIFT = 0;
+    static constexpr bool HALO = false;
+    static constexpr bool PARTIAL = true;
+    __host__ __device__ static int off(int) { return 0; }
     __device__ static int len(int, int n, const SweepJob &) { return n; }
-    __device__ static int tab_index(int) { return 3; }
-    __device__ static int tab_len(int, int n) { return n - 2; }
-    struct State {
-        const double *tsm;
-        int H;
+    __host__ __device__ static int tab_index(int) { return 3; }
+    __host__ __device__ static int tab_len(int, int n) { return n - 2; }
+    struct State : TAB {
         double x;
     };
     __device__ static void init(State &s, const SweepJob &, int, int) { s.x = 0.0; }
@@ -419,18 +446,21 @@ struct TdmaBwd {
 };
 
 // fdma.f90:26-36: forward x_i -= l_{i-2} x_{i-2}; job.tab: 0 = l, 1 = d, 2 = u1, 3 = u2, 4 = RN(1/d) (optional)
-template <bool FULL>
+template <bool FULL, class TAB = TabParity>
 struct FdmaFwd {
     static constexpr int NIN = 1;
     static constexpr int NT = 1;
     static constexpr bool ASC = true;
-    __device__ static int off(int) { return 0; }
+    // k_sweep_tile: step index of output k is k + ISHIFT; HALO: reads input element i + 2 (or k + 1);
+    // PARTIAL: some indices are not stored (in place only: the tile is pre-filled with the input)
+    static constexpr int ISHIFT = 0;
+    static constexpr bool HALO = false;
+    static constexpr bool PARTIAL = true;
+    __host__ __device__ static int off(int) { return 0; }
     __device__ static int len(int, int n, const SweepJob &) { return n; }
-    __device__ static int tab_index(int) { return 0; }
-    __device__ static int tab_len(int, int n) { return n - 2; }
-    struct State {
-        const double *tsm;
-        int H;
+    __host__ __device__ static int tab_index(int) { return 0; }
+    __host__ __device__ static int tab_len(int, int n) { return n - 2; }
+    struct State : TAB {
         double p;
     };
     __device__ static void init(State &s, const SweepJob &, int, int) { s.p = 0.0; }
@@ -446,18 +476,21 @@ struct FdmaFwd {
     }
 };
 
-template <bool FULL>
+template <bool FULL, class TAB = TabParity>
 struct FdmaBwd {
     static constexpr int NIN = 1;
     static constexpr int NT = 4;          // staged: 0 = d, 1 = u1, 2 = u2, 3 = rd
     static constexpr bool ASC = false;
-    __device__ static int off(int) { return 0; }
+    // k_sweep_tile: step index of output k is k + ISHIFT; HALO: reads input element i + 2 (or k + 1);
+    // PARTIAL: some indices are not stored (in place only: the tile is pre-filled with the input)
+    static constexpr int ISHIFT = 0;
+    static constexpr bool HALO = false;
+    static constexpr bool PARTIAL = false;
+    __host__ __device__ static int off(int) { return 0; }
     __device__ static int len(int, int n, const SweepJob &) { return n; }
-    __device__ static int tab_index(int k) { return k + 1; }
-    __device__ static int tab_len(int k, int n) { return k == 1 ? n - 2 : (k == 2 ? n - 4 : n); }
-    struct State {
-        const double *tsm;
-        int H;
+    __host__ __device__ static int tab_index(int k) { return k + 1; }
+    __host__ __device__ static int tab_len(int k, int n) { return k == 1 ? n - 2 : (k == 2 ? n - 4 : n); }
+    struct State : TAB {
         double x2, x4;     // x_{i+2}, x_{i+4} of this chain
         bool has_r;
     };
@@ -481,18 +514,21 @@ struct FdmaBwd {
 };
 
 // twodma.f90:17-22; job.tab: 0 = d, 1 = u, 4 = RN(1/d) (optional)
-template <bool FULL>
+template <bool FULL, class TAB = TabParity>
 struct TwodmaBwd {
     static constexpr int NIN = 1;
     static constexpr int NT = 3;          // staged: 0 = d, 1 = u, 2 = rd
     static constexpr bool ASC = false;
-    __device__ static int off(int) { return 0; }
+    // k_sweep_tile: step index of output k is k + ISHIFT; HALO: reads input element i + 2 (or k + 1);
+    // PARTIAL: some indices are not stored (in place only: the tile is pre-filled with the input)
+    static constexpr int ISHIFT = 0;
+    static constexpr bool HALO = false;
+    static constexpr bool PARTIAL = false;
+    __host__ __device__ static int off(int) { return 0; }
     __device__ static int len(int, int n, const SweepJob &) { return n; }
-    __device__ static int tab_index(int k) { return k == 2 ? 4 : k; }
-    __device__ static int tab_len(int k, int n) { return k == 1 ? n - 2 : n; }
-    struct State {
-        const double *tsm;
-        int H;
+    __host__ __device__ static int tab_index(int k) { return k == 2 ? 4 : k; }
+    __host__ __device__ static int tab_len(int k, int n) { return k == 1 ? n - 2 : n; }
+    struct State : TAB {
         double x;
         bool has_r;
     };
@@ -516,18 +552,16 @@ struct TwodmaBwd {
 // Poisson (A + lam_q C) columns with per-column LU tables (n x m arrays, same layout as x):
 // streams: 0 = x, 1 = L (read at i-2);  itab[q] = 1 where the singular branch drops row/col 0
 // (fdma.f90:173-185): that column's system starts at i = 1 and x[0] = 0.
-template <bool FULL>
+template <bool FULL, class TAB = TabParity>
 struct PoissonFwd {
     static constexpr int NIN = 2;
     static constexpr int NT = 0;
     static constexpr bool ASC = true;
-    __device__ static int off(int s) { return s == 0 ? 0 : -2; }
+    __host__ __device__ static int off(int s) { return s == 0 ? 0 : -2; }
     __device__ static int len(int, int n, const SweepJob &) { return n; }
-    __device__ static int tab_index(int) { return 0; }
-    __device__ static int tab_len(int, int) { return 0; }
-    struct State {
-        const double *tsm;
-        int H;
+    __host__ __device__ static int tab_index(int) { return 0; }
+    __host__ __device__ static int tab_len(int, int) { return 0; }
+    struct State : TAB {
         double p;
         int off;
     };
@@ -553,18 +587,16 @@ struct PoissonFwd {
 };
 
 // streams: 0 = x, 1 = D, 2 = U1, 3 = U2, 4 = RN(1/D)
-template <bool FULL>
+template <bool FULL, class TAB = TabParity>
 struct PoissonBwd {
     static constexpr int NIN = 5;
     static constexpr int NT = 0;
     static constexpr bool ASC = false;
-    __device__ static int off(int) { return 0; }
+    __host__ __device__ static int off(int) { return 0; }
     __device__ static int len(int, int n, const SweepJob &) { return n; }
-    __device__ static int tab_index(int) { return 0; }
-    __device__ static int tab_len(int, int) { return 0; }
-    struct State {
-        const double *tsm;
-        int H;
+    __host__ __device__ static int tab_index(int) { return 0; }
+    __host__ __device__ static int tab_len(int, int) { return 0; }
+    struct State : TAB {
         double x2, x4;
         int off;
     };
@@ -586,6 +618,212 @@ struct PoissonBwd {
         s.x2 = x;
     }
 };
+
+
+// ---------------------------------------------------------------------------
+// TS sweeps, tiled: k_sweep_tile
+// ---------------------------------------------------------------------------
+// k_sweep<Op, TS> gives every lane its own row and streams it with 8-byte copies: DRAM sees isolated
+// 32-byte sectors of 32 rows per warp step, each parity chain is a separate warp on another SM (both fetch
+// every sector), and a chain step costs ~28 instructions of ONE warp (ncu: 1.3-1.7 TB/s, IPC 0.3-0.45).
+// Here a warp owns 32 rows and moves them tile by tile (TILE_W = 64 elements of every row):
+//   * load: 32 + 1 cp.async instructions, each one contiguous 512-byte row segment (lane l copies the
+//     16-byte pair l), NST - 1 tiles in flight per warp; the per-index tables of the tile ride along;
+//   * chain: the CTA is two warps, warp w walks the parity-w chain of row `lane` in shared memory (the first
+//     version put both chains into one thread: half as many warps, each with twice the instruction stream --
+//     slower, because these kernels are bound by the issue latency of the few resident warps);
+//   * store: the output tile goes back as 32 contiguous 512-byte row segments.
+// Same Op::step as k_sweep, so the arithmetic (and every bit of the result) is unchanged.
+__device__ __forceinline__ void cp_async_16z(double *smem, const double *gmem, int src_bytes)
+{
+    unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "r"(src_bytes) : "memory");
+}
+
+struct TileWriter {
+    double *row;       // this lane's row of the output tile
+    int base;          // index of its first element
+    template <bool MID = false>
+    __device__ __forceinline__ void st(int i, double v) const { row[i - base] = v; }
+};
+
+template <class Op>
+struct TileStage {
+    static constexpr int value = 32 * TILE_P + ((Op::NT * TILE_TP + 1) & ~1);    // doubles: rows + table slices
+};
+
+template <class Op, int NST>
+__global__ void __launch_bounds__(64) k_sweep_tile(SweepJobs jobs)
+{
+    extern __shared__ __align__(16) double tsm_[];
+    constexpr int TW = TILE_W, TP = TILE_P, TTP = TILE_TP, NT = Op::NT;
+    constexpr int STAGE = TileStage<Op>::value;
+    constexpr int IS = Op::ISHIFT;
+    const SweepJob &job = jobs.j[blockIdx.y];
+    // two warps per CTA: warp w walks the chain of parity w of the CTA's 32 rows (lane = row) and moves rows
+    // 16 w .. 16 w + 15 of every tile (lane = 16-byte pair of the row segment)
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5, q0 = blockIdx.x * 32;
+    if (q0 >= job.nseq) return;
+    const int n = jobs.n;
+    const int nrows = min(32, job.nseq - q0);
+    const unsigned ldi = (unsigned)job.ldin[0], ldo = (unsigned)job.ldout;
+    const int r_lo = 16 * wrp, r_hi = min(r_lo + 16, nrows);          // rows this warp copies
+    const double *gin = job.in[0] + (long)q0 * ldi;
+    double *gout = job.out + (long)q0 * ldo;
+    const int in_len = (Op::HALO && IS == 0) ? (job.in[1] ? n + 2 : n) : n;     // TdmaFwd reads u_{i+2} of the n + 2 inputs
+    const int ntiles = (n + TW - 1) / TW;
+    double *out_tile = tsm_ + NST * STAGE;
+
+    auto issue = [&](int u) {
+        if (u >= ntiles) return;
+        const int tbase = (Op::ASC ? u : ntiles - 1 - u) * TW;
+        double *ti = tsm_ + (u % NST) * STAGE;
+        const int col = tbase + 2 * lane;
+        const int nb = col < in_len ? 16 : 0;
+        const double *g = gin + (nb ? col : 0);
+        double *d = ti + 2 * lane;
+        if (r_hi - r_lo == 16) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+                cp_async_16z(d + (r_lo + r) * TP, g + (unsigned long long)((unsigned)(r_lo + r) * ldi), nb);
+        } else {
+            for (int r = r_lo; r < r_hi; ++r) cp_async_16z(d + r * TP, g + (unsigned long long)((unsigned)r * ldi), nb);
+        }
+        if (Op::HALO && wrp == 0 && lane < nrows) {
+            const int ch = tbase + TW;
+            cp_async_16z(ti + lane * TP + TW, gin + (unsigned long long)((unsigned)lane * ldi) + (ch < in_len ? ch : 0),
+                         ch < in_len ? 16 : 0);
+        }
+        if (NT > 0 && wrp == 1) {
+            double *tt = ti + 32 * TP;
+#pragma unroll
+            for (int k = 0; k < NT; ++k) {
+                const double *tp = job.tab[Op::tab_index(k)];
+                const int tl = tp ? Op::tab_len(k, n) : 0;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int pr = lane + 32 * h;                 // pair of the slice [tbase - 2, tbase + TW + 2)
+                    if (pr >= TTP / 2) break;
+                    const int e0 = tbase - 2 + 2 * pr;
+                    const int nbt = (e0 >= 0 && e0 + 1 < tl) ? 16 : ((e0 >= 0 && e0 < tl) ? 8 : 0);
+                    cp_async_16z(tt + k * TTP + 2 * pr, nbt ? tp + e0 : gin, nbt);
+                }
+            }
+        }
+    };
+
+    typename Op::State st;
+    Op::init(st, job, n, q0 + lane);
+    const bool active = lane < nrows;
+
+#pragma unroll 1
+    for (int u = 0; u < NST - 1; ++u) {
+        issue(u);
+        cp_async_commit_group();
+    }
+#pragma unroll 1
+    for (int u = 0; u < ntiles; ++u) {
+        cp_async_wait_group<NST - 2>();
+        __syncthreads();         // tile u has landed for every thread; everybody is done with tile u - 1 (in and out)
+        issue(u + NST - 1);
+        cp_async_commit_group();
+        const int tbase = (Op::ASC ? u : ntiles - 1 - u) * TW;
+        const double *ti = tsm_ + (u % NST) * STAGE;
+        const double *rin = ti + lane * TP;
+        TileWriter out{out_tile + lane * TP, tbase};
+        st.tt = ti + 32 * TP;
+        st.i0 = tbase;
+        // all steps of an interior tile satisfy 8 <= i <= n - 9: no edge logic (Op::step<true>)
+        const bool mid = tbase >= 8 && tbase + TW + IS + 8 <= n;
+        if (active) {
+            if (Op::PARTIAL) {                                // unstored indices keep the input (in place)
+                if (!mid) {
+#pragma unroll 8
+                    for (int j = wrp; j < TW; j += 2) out_tile[lane * TP + j] = rin[j];
+                }
+            }
+            // output k = tbase + e has step index i = k + IS; this warp takes the i of its parity
+            const int e0 = (wrp + IS) & 1;                    // first e of this warp's parity (tbase is even)
+            auto block = [&](int b, auto mid_tag) {           // 8 of the 16 outputs e = 16 b .. 16 b + 15
+                constexpr bool MID = decltype(mid_tag)::value;
+                const double *rb = rin + 16 * b + e0 + IS;   // input element of step e = 16 b + e0
+                const int ib = tbase + 16 * b + e0 + IS;
+                double v[8][Op::NIN];
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+#pragma unroll
+                    for (int s = 0; s < Op::NIN; ++s) v[t][s] = rb[2 * t + Op::off(s)];
+                static_for<0, 8>([&](auto tc) {
+                    constexpr int t = Op::ASC ? decltype(tc)::value : 7 - decltype(tc)::value;
+                    const int i = ib + 2 * t;
+                    if (MID || (i >= 0 && i < n)) Op::template step<MID>(st, job, n, i, v[t], out);
+                });
+            };
+#pragma unroll 1
+            for (int bb = 0; bb < TW / 16; ++bb) {
+                const int b = Op::ASC ? bb : TW / 16 - 1 - bb;
+                if (mid) block(b, std::true_type{});
+                else block(b, std::false_type{});
+            }
+        }
+        __syncthreads();
+        // store: row r of the tile = one contiguous segment of <= 512 bytes
+        const int cnt = min(TW, n - tbase);
+        if (2 * lane < cnt) {
+            const double *src = out_tile + 2 * lane;
+            double *dst = gout + tbase + 2 * lane;
+            if (r_hi - r_lo == 16) {
+#pragma unroll
+                for (int r = 0; r < 16; ++r)
+                    *reinterpret_cast<double2 *>(dst + (unsigned long long)((unsigned)(r_lo + r) * ldo)) =
+                        *reinterpret_cast<const double2 *>(src + (r_lo + r) * TP);
+            } else {
+                for (int r = r_lo; r < r_hi; ++r)
+                    *reinterpret_cast<double2 *>(dst + (unsigned long long)((unsigned)r * ldo)) =
+                        *reinterpret_cast<const double2 *>(src + r * TP);
+            }
+        }
+    }
+}
+
+// eligibility of the tiled TS kernel: even lengths and pitches, 16-byte aligned rows and tables, one input array
+template <class Op>
+static bool sweep_tile_ok(const SweepJobs &jobs)
+{
+    auto al = [](const void *q) { return ((uintptr_t)q % 16) == 0; };
+    if (jobs.n % 2 != 0 || jobs.n < 2 * TILE_W) return false;
+    for (int j = 0; j < jobs.njobs; ++j) {
+        const SweepJob &jb = jobs.j[j];
+        if (!jb.in[0] || !jb.out || !al(jb.in[0]) || !al(jb.out) || jb.ldin[0] % 2 || jb.ldout % 2) return false;
+        if (jb.ldin[0] >= (1L << 26) || jb.ldout >= (1L << 26)) return false;      // 32-bit row offsets
+        for (int s = 1; s < Op::NIN; ++s)
+            if (jb.in[s] && (jb.in[s] != jb.in[0] || jb.ldin[s] != jb.ldin[0])) return false;
+        for (int k = 0; k < Op::NT; ++k)
+            if (jb.tab[Op::tab_index(k)] && !al(jb.tab[Op::tab_index(k)])) return false;
+        if (Op::PARTIAL && jb.out != jb.in[0]) return false;                  // unstored indices keep the input
+        if (Op::HALO && !Op::ASC && jb.out == jb.in[0]) return false;         // the halo of a later tile would be overwritten
+    }
+    return true;
+}
+
+template <template <bool, class> class OpT, bool FULL>
+static int launch_sweep_tile(const SweepJobs &jobs, cudaStream_t st, const char *what)
+{
+    using Op = OpT<FULL, TabTile>;
+    constexpr int NST = 3;
+    int maxseq = 0;
+    for (int j = 0; j < jobs.njobs; ++j) maxseq = jobs.j[j].nseq > maxseq ? jobs.j[j].nseq : maxseq;
+    if (maxseq <= 0) return PDE_OK;
+    const size_t smem = ((size_t)NST * TileStage<Op>::value + 32 * TILE_P) * sizeof(double);
+    static bool attr = false;
+    if (!attr) {
+        PDE_CUDA(cudaFuncSetAttribute(k_sweep_tile<Op, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = true;
+    }
+    dim3 grid(ceil_div(maxseq, 32), jobs.njobs);
+    k_sweep_tile<Op, NST><<<grid, 64, smem, st>>>(jobs);
+    return after_launch(what);
+}
 
 template <class Op>
 static int launch_sweep(const SweepJobs &jobs, int axis, cudaStream_t st, const char *what)

@@ -380,3 +380,124 @@ def test_batched_diff_sweep_bit_exact(dev, axis, scales):
     torch.cuda.synchronize()
     for k, ref in enumerate(refs):
         assert np.array_equal(H(keep[2 * k + 1]), ref), "job %d" % k
+
+
+@pytest.mark.parametrize("axis", [0, 1])
+@pytest.mark.parametrize("offsets", [(0, 2, 4), (-2, 0, 2, 4), (0,), (-1, 0, 3)])
+@pytest.mark.parametrize("accumulate", [False, True])
+def test_banded_multi_bit_exact(dev, axis, offsets, accumulate):
+    """pde_banded_multi (the stepper's batched PlanRHS products, solver/plans.py:54-74, matrix.py:48-53): jobs of
+    different shapes in one launch.  Even sizes with diagonals off0, off0+2, ... take the strip kernels, the
+    (-1, 0, 3) pattern and the odd-sized job the generic kernel; all must equal the NumPy expression
+    sum_d diag_d * x[row + off_d] (products and sums rounded separately, ascending d) bit for bit."""
+    import torch
+    from pypde_b200 import _cabi as C
+    rng = np.random.default_rng(17 + axis)
+    if offsets == (-2, 0, 2, 4):
+        shapes = [(70, 70, 130), (34, 34, 64), (6, 6, 2)]          # strip kernels (square B S operators)
+    elif offsets == (0, 2, 4):
+        shapes = [(70, 72, 130), (34, 36, 64), (2, 4, 258)]        # strip kernels (B(2,2): n_in = n_out + 2)
+    else:
+        shapes = [(70, 72, 130), (34, 36, 64), (33, 35, 7)]        # generic kernel (odd job / other pattern)
+    arr = (C.BandJob * len(shapes))()
+    keep, refs = [], []
+    for k, (n_out, n_in, batch) in enumerate(shapes):
+        diags = rng.standard_normal((len(offsets), n_out))
+        diags[:, min(3, n_out - 1)] = 0.0                       # zero coefficients are skipped
+        x = rng.standard_normal((n_in, batch) if axis == 0 else (batch, n_in))
+        y0 = rng.standard_normal((n_out, batch) if axis == 0 else (batch, n_out))
+        xs = x if axis == 0 else x.T
+        acc = np.zeros((n_out, batch))
+        for d, off in enumerate(offsets):
+            for r in range(n_out):
+                c = r + off
+                if 0 <= c < n_in and diags[d, r] != 0.0:
+                    acc[r] = acc[r] + diags[d, r] * xs[c]
+        ref = acc if axis == 0 else acc.T
+        refs.append(y0 + ref if accumulate else ref)
+        dx, dy, dd = T(x, dev), T(y0, dev), T(diags, dev)
+        keep += [dx, dy, dd]
+        j = arr[k]
+        j.diags, j.ndiag = dd.data_ptr(), len(offsets)
+        for d, off in enumerate(offsets):
+            j.off[d] = off
+        j.x, j.ldx, j.n_in = dx.data_ptr(), dx.stride(0), n_in
+        j.y, j.ldy, j.n_out = dy.data_ptr(), dy.stride(0), n_out
+        j.batch, j.accumulate = batch, int(accumulate)
+    C.check(C.lib().pde_banded_multi(axis, len(shapes), arr, C.stream()))
+    torch.cuda.synchronize()
+    for k, ref in enumerate(refs):
+        assert np.array_equal(H(keep[3 * k + 1]), ref), "job %d" % k
+
+
+def _sweep_jobs(C, jobs):
+    """jobs: dicts with in (list), out, tab {slot: tensor}, nseq, flag, sc -> ctypes array (kept alive by the caller)"""
+    arr = (C.SweepJob * len(jobs))()
+    for k, jb in enumerate(jobs):
+        j = arr[k]
+        for s, t in enumerate(jb["in"]):
+            j.inp[s], j.ldin[s] = t.data_ptr(), t.stride(0)
+        j.out, j.ldout = jb["out"].data_ptr(), jb["out"].stride(0)
+        for slot, t in jb.get("tab", {}).items():
+            j.tab[slot] = t.data_ptr()
+        j.nseq, j.flag, j.sc = jb["nseq"], int(jb.get("flag", 0)), float(jb.get("sc", 1.0))
+    return arr
+
+
+@pytest.mark.parametrize("n", [128, 256, 330, 2046])
+def test_tiled_row_sweeps_bit_exact(dev, n):
+    """Axis-1 sweeps at even lengths >= 128 take the tiled kernel (k_sweep_tile: 32 rows per warp, 64-element tiles,
+    both parity chains per thread).  Every operator of the stepper, batched over jobs of ragged widths, against the
+    oracle's Fortran restatements: differentiate_cheby.f90:28-53, tdma.f90:55-106 (+ S^T, chebyshev.py:327),
+    fdma.f90:40-98.  Bit for bit."""
+    import torch
+    from pypde_b200 import Base, _cabi as C
+    from oracle import kernels as K, pypde_port as P
+    rng = np.random.default_rng(n)
+    widths = (70, 33, 1) if n < 2000 else (40, 9)
+    DIFF, TDMA_FWD, TDMA_BWD, FDMA_FWD, FDMA_BWD = 0, 1, 2, 3, 4
+    run = lambda op, nn, jobs: C.check(C.lib().pde_sweep(op, 1, nn, len(jobs), _sweep_jobs(C, jobs), C.stream()))
+    # derivative, scale 1/2 (power of two) -> the reference's diff_2d(c) / 0.5
+    cs = [rng.standard_normal((w, n)) for w in widths]
+    xs = [T(c, dev) for c in cs]
+    ys = [torch.full(c.shape, np.nan, dtype=torch.float64, device=dev) for c in cs]
+    run(DIFF, n, [dict(**{"in": [x]}, out=y, nseq=x.shape[0], flag=1, sc=0.5) for x, y in zip(xs, ys)])
+    for c, y in zip(cs, ys):
+        assert np.array_equal(H(y), K.diff_2d(np.ascontiguousarray(c.T)).T / 0.5)
+    # from_chebyshev = S^T + offset-2 tridiagonal solve: n + 2 Chebyshev coefficients -> n Galerkin coefficients
+    for kind in ("CD", "CN"):
+        b, o = Base(n + 2, kind), P.Basis(n + 2, kind)
+        s, a, den, w = b._tables()
+        rden = 1.0 / den
+        us = [rng.standard_normal((wd, n + 2)) for wd in widths]
+        du = [T(u, dev) for u in us]
+        dv = [torch.full((u.shape[0], n), np.nan, dtype=torch.float64, device=dev) for u in us]
+        run(TDMA_FWD, n, [dict(**{"in": [u, u]}, out=v, nseq=u.shape[0], tab={0: s, 1: a, 2: den, 4: rden})
+                          for u, v in zip(du, dv)])
+        run(TDMA_BWD, n, [dict(**{"in": [v]}, out=v, nseq=v.shape[0], tab={3: w}) for v in dv])
+        # oracle sweep (tdma.f90) on the product's own diagonals: at N = 514 / 2048 the reference's dense BLAS
+        # product S^T S (chebyshev.py:339-345) rounds 1 + s_k^2 twice for one or two k, depending on the host's
+        # BLAS blocking; the product rounds it once for every k (DESIGN.md section 2) -- this test pins the kernels
+        l2, dd, u2 = b._init_stencil_inv()
+        sd = b.stencil_diag().copy()
+        sd[np.abs(sd) < 1e-12] = 0
+        for u, v in zip(us, dv):
+            rhs = u[:, :n] + sd[:n] * u[:, 2:]
+            assert np.array_equal(H(v), K.solve_tdma_2d(l2, dd, u2, np.ascontiguousarray(rhs.T), 2).T), kind
+            if n <= 330:
+                assert np.array_equal(H(v), o.from_cheb(np.ascontiguousarray(u.T)).T), kind
+    # 4-diagonal solve, forward in place, back substitution into a second array (the stepper's last sweep)
+    A = np.zeros((n, n))
+    for off in (-2, 0, 2, 4):
+        A += np.diag(rng.standard_normal(n - abs(off)) * 0.3 + (3.0 if off == 0 else 0.0), off)
+    l, d, u1, u2 = P.fdma_lu(A)
+    tl, td, tu1, tu2, trd = (C.upload(t) for t in (l, d, u1, u2, 1.0 / d))
+    bs = [rng.standard_normal((wd, n)) for wd in widths]
+    dx = [T(bb, dev) for bb in bs]
+    dy = [torch.full(bb.shape, np.nan, dtype=torch.float64, device=dev) for bb in bs]
+    run(FDMA_FWD, n, [dict(**{"in": [x]}, out=x, nseq=x.shape[0], tab={0: tl}) for x in dx])
+    run(FDMA_BWD, n, [dict(**{"in": [x]}, out=y, nseq=x.shape[0], tab={1: td, 2: tu1, 3: tu2, 4: trd})
+                      for x, y in zip(dx, dy)])
+    torch.cuda.synchronize()
+    for bb, y in zip(bs, dy):
+        assert np.array_equal(H(y), K.solve_fdma_2d(l, d, u1, u2, bb.copy(), 1))
