@@ -219,6 +219,16 @@ template <int P, int M1, int NCUR, int S, int T, int... RAD>
 struct DifPasses : DifPassesW<0, -1, P, M1, NCUR, S, T, RAD...> {
 };
 
+// the passes after the first one (the fused load + first pass of k_dct_fft_t runs the first itself)
+template <int R1, int... Rest>
+struct TailPasses {
+    template <int SP, int P, int M1, int S, int T>
+    __device__ __forceinline__ static void run(double2 *z, const double2 *__restrict__ W)
+    {
+        if constexpr (sizeof...(Rest) > 0) DifPassesW<SP, (R1 - 1) * (P / R1), P, M1, P / R1, S, T, Rest...>::run(z, W);
+    }
+};
+
 // host: the [r][j] tables of all passes, concatenated in pass order (offsets as in DifPassesW)
 template <int R, int... Rest>
 static void build_pass_tables(int P, int ncur, std::vector<double2> &out)
@@ -309,6 +319,56 @@ k_dct_fft_t(const double2 *__restrict__ W, const double2 *__restrict__ CS, int m
         v1 *= so;
         dst = s * PS + PD::phys(m);
     };
+    // Axis 1, one sequence per CTA, one first-pass butterfly per thread: the butterfly's 16 inputs
+    // z_m, m = j + r M1, are read straight from global memory (lanes j -> consecutive 16-byte pairs: coalesced; the
+    // zero-padded part of a backward transform is never read), so the load phase's shared-memory store and the first
+    // pass's shared-memory load -- 2 of the kernel's ~10 sweeps over the 48 KB sequence -- and one barrier disappear.
+    // MEASURED (B200, 2048 x 3073, backward): 0.060 ms fused vs 0.059 ms unfused -- the exposed global latency of the
+    // butterfly's 32 loads eats what the saved shared-memory traffic gives, so this stays opt-in (-DPDE_FFT_FUSE1);
+    // parity tests pass with it (156 GPU tests).
+#ifndef PDE_FFT_FUSE1
+    constexpr bool FUSE1 = false;
+#else
+    constexpr bool FUSE1 = AXIS == 1 && S == 1 && FirstRadix<RAD...>::value == 16 && T == P / 16 && sizeof...(RAD) >= 2;
+#endif
+    if constexpr (FUSE1) {
+        constexpr int R = 16, M = P / R;
+        const int j = threadIdx.x;
+        const double *src = x + (long)q0 * ldx;
+        const bool vec = ((ldx & 1) == 0) && (((unsigned long long)x & 15) == 0);
+        double2 a[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int m = j + r * M;
+            double v0, v1;
+            if (r < R / 2) {                                   // m < P/2: (x_2m, x_2m+1)
+                const int n0 = 2 * m;
+                if (vec && n0 + 1 < n_in) {
+                    const double2 t = __ldg(reinterpret_cast<const double2 *>(src + n0));
+                    v0 = t.x;
+                    v1 = t.y;
+                } else {
+                    v0 = n0 < n_in ? __ldg(src + n0) : 0.0;
+                    v1 = n0 + 1 < n_in ? __ldg(src + n0 + 1) : 0.0;
+                }
+            } else {                                           // m >= P/2: (x_{2P-2m}, x_{2P-2m-1})
+                const int n0 = 2 * P - 2 * m;
+                v0 = n0 < n_in ? __ldg(src + n0) : 0.0;
+                v1 = n0 - 1 < n_in ? __ldg(src + n0 - 1) : 0.0;
+            }
+            // the end points x_0 (m = 0) and x_P (m = P/2, even slot) are not scaled
+            const bool edge = (r == 0 || r == R / 2) && j == 0;
+            a[r] = make_double2(v0 * (edge ? 1.0 : se), v1 * so);
+        }
+        dft<R>(a);
+#pragma unroll
+        for (int r = 1; r < R; ++r) a[r] = cmul(a[r], __ldg(W + (r - 1) * M + j));
+        double2 *p = zsm + j;
+#pragma unroll
+        for (int r = 0; r < R; ++r) p[r * (M + 1)] = a[r];
+        __syncthreads();
+        TailPasses<RAD...>::template run<SP, P, M1, S, T>(zsm, W);
+    } else {
     if (ns == S) {
         // Full CTA.  The iteration index is a compile-time constant and the thread index enters through
         // per-thread invariants, so the (sequence, element) split costs nothing per element (the generic
@@ -370,6 +430,7 @@ k_dct_fft_t(const double2 *__restrict__ W, const double2 *__restrict__ CS, int m
     }
     __syncthreads();
     DifPassesW<SP, 0, P, M1, P, S, T, RAD...>::run(zsm, W);      // W: per-pass [r][j] tables (p->Wp)
+    }
 
     // ---- split + store
     const double fs = 1.0 / (2.0 * (double)P);
