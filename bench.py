@@ -451,11 +451,13 @@ def run_gpu(args, cfg):
     roof_dct = {"kernel": "k_dct_fft (shared-memory FFT DCT-I, all batched transforms of the step)", "bound": "hbm",
                 "achieved": dct_work / (dct_ms * 1e-3) / 1e9 if dct_ms else None, "peak": peaks.get("hbm_gbs"),
                 "unit": "GB/s",
-                "traffic": 61757696,
-                "traffic_note": "ncu --set full of k_dct_fft_t<3072,1,192,1,...> on ONE 2048-sequence array "
-                                "(tools/prof_dct.py, profiles/r01_ncu_dct_fft_specialised_v1.csv): dram read 50.4 MB + "
-                                "write 11.3 MB against 100.7 MB algorithmic (the 50 MB output stays in the 126 MB L2); "
-                                "the bench launches carry 3-8 such arrays",
+                "traffic": 548850000,
+                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the four DCT "
+                                "launches of one stage (ncu --set full of an eager rbc2048 stage, "
+                                "profiles/r01_ncu_stage_final.csv: 8 backward arrays along axis 0 634 MB, 8 backward "
+                                "along axis 1 982 MB, 3 forward along axis 1 352 MB, 3 forward along axis 0 227 MB) "
+                                "against 692 MB algorithmic per launch: below it because part of each array is still "
+                                "in the 126 MB L2 from the producing kernel; no re-reads",
                 "peak_source": peak_src, "launches_per_step": dct_launches,
                 "avg_launch_ms": dct_ms / max(dct_launches, 1), "share_of_step": dct_ms / step_ms_instr,
                 "algorithmic_bytes_per_launch": dct_work / max(dct_launches, 1)}

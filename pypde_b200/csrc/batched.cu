@@ -103,13 +103,22 @@ __global__ void __launch_bounds__(256, 4) k_banded_multi(BandJobs jobs, int axis
 //   axis 1 (taps along the contiguous axis): the coefficients of the two columns are loaded once per thread and
 //           reused over RS1 rows; the taps of a row are nd aligned 16-byte loads.
 // Same products, same order of sums, zero coefficients skipped: bit-identical to k_banded_multi.
-constexpr int RS0 = 4, RS1 = 4;
+#ifndef PDE_BAND_RS0
+#define PDE_BAND_RS0 4
+#endif
+#ifndef PDE_BAND_RS1
+#define PDE_BAND_RS1 4
+#endif
+#ifndef PDE_BAND_MINB
+#define PDE_BAND_MINB 2
+#endif
+constexpr int RS0 = PDE_BAND_RS0, RS1 = PDE_BAND_RS1;
 
 __device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
 __device__ __forceinline__ double2 ldg2(const double *p) { return __ldg(reinterpret_cast<const double2 *>(p)); }
 
 template <int AXIS>
-__global__ void __launch_bounds__(256, 2) k_banded_strip(BandJobs jobs)
+__global__ void __launch_bounds__(256, PDE_BAND_MINB) k_banded_strip(BandJobs jobs)
 {
     const pde_band_job &jb = jobs.j[blockIdx.z];
     const int n0 = AXIS == 0 ? jb.n_out : jb.batch, n1 = AXIS == 0 ? jb.batch : jb.n_out;
