@@ -14,7 +14,7 @@
 namespace pde {
 
 // inverse of dif_pass_t: x = IDFT_R( conj(W^{j r}) y_r ) (the 1/R factors are folded into Bhat)
-template <int P, int M1, int NCUR, int S, int T, int R>
+template <int WOFF, int P, int M1, int NCUR, int S, int T, int R>
 __device__ __forceinline__ void dit_pass_t(double2 *z, const double2 *__restrict__ W)
 {
     constexpr int M = NCUR / R, PER_SEQ = P / R, TOTAL = S * PER_SEQ, TWS = P / NCUR;
@@ -26,17 +26,29 @@ __device__ __forceinline__ void dit_pass_t(double2 *z, const double2 *__restrict
         if ((TOTAL % T) != 0 && b >= TOTAL) break;
         const int s = b / PER_SEQ;
         const int bb = b - s * PER_SEQ;
-        const int blk = bb / M;
-        const int j = bb - blk * M;
-        const int i0 = blk * NCUR + j;
-        double2 *p = z + s * PS + (NCUR == P ? i0 : Pad<P, M1>::phys(i0));
+        // same conflict-free thread -> butterfly map as dif_pass_t (dct_fft_t.cuh): consecutive butterflies walk
+        // the first-level blocks (pitch M1 + 1), j is the slow index.  With j fastest the last-level pass
+        // (NCUR = 16: addresses 16 b + r) was an 8-way bank conflict (tools/sim_fft_banks.py).
+        constexpr int R1 = P / M1, NBLK = P / NCUR;
+        int j, off;
+        if (NCUR == P) {
+            j = bb;
+            off = bb;
+        } else {
+            j = bb / NBLK;
+            const int bi = bb - j * NBLK;
+            const int first = bi % R1, inner = bi / R1;
+            off = first * (M1 + 1) + inner * NCUR + j;
+        }
+        double2 *p = z + s * PS + off;
         double2 a[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) a[r] = p[r * RS];
         if (M > 1) {
 #pragma unroll
             for (int r = 1; r < R; ++r) {
-                const double2 w = __ldg(W + j * (r * TWS));
+                // per-pass [r][j] tables (same entries as W[j r TWS]; coalesced / broadcast instead of strided)
+                const double2 w = WOFF < 0 ? __ldg(W + j * (r * TWS)) : __ldg(W + WOFF + (r - 1) * M + j);
                 a[r] = make_double2(a[r].x * w.x + a[r].y * w.y, a[r].y * w.x - a[r].x * w.y);   // * conj(w)
             }
         }
@@ -50,12 +62,13 @@ __device__ __forceinline__ void dit_pass_t(double2 *z, const double2 *__restrict
 }
 
 // passes in reverse order of DifPasses<P, M1, P, S, T, RAD...>
-template <int P, int M1, int NCUR, int S, int T, int R, int... Rest>
+template <int WOFF, int P, int M1, int NCUR, int S, int T, int R, int... Rest>
 struct DitPasses {
     __device__ __forceinline__ static void run(double2 *z, const double2 *__restrict__ W)
     {
-        if constexpr (sizeof...(Rest) > 0) DitPasses<P, M1, NCUR / R, S, T, Rest...>::run(z, W);
-        dit_pass_t<P, M1, NCUR, S, T, R>(z, W);
+        constexpr int NEXT = WOFF < 0 ? -1 : WOFF + (NCUR / R > 1 ? (R - 1) * (NCUR / R) : 0);   // as DifPassesW
+        if constexpr (sizeof...(Rest) > 0) DitPasses<NEXT, P, M1, NCUR / R, S, T, Rest...>::run(z, W);
+        dit_pass_t<WOFF, P, M1, NCUR, S, T, R>(z, W);
         __syncthreads();
     }
 };
@@ -65,6 +78,7 @@ struct BluesteinTables {
     const double2 *chirp;   // c_m = exp(i pi m^2 / P), m < P
     const double2 *Bhat;    // FFT_M of the wrapped chirp / M, in digit-reversed (DIF output) order
     const double2 *CS;      // (cos, sin)(pi k / P), k <= (P+1)/2
+    const double2 *Wp;      // per-pass [r][j] twiddle tables of the length-M FFT (built at the first launch)
 };
 
 template <int M, int S, int T, int AXIS, int... RAD>
@@ -111,7 +125,7 @@ k_dct_bluestein(BluesteinTables tb, int P, int mode, DctPtrs ptrs, long ldx, int
         zsm[s * PS + PD::phys(m)] = a;
     }
     __syncthreads();
-    DifPasses<M, M1, M, S, T, RAD...>::run(zsm, tb.W);
+    DifPassesW<0, 0, M, M1, M, S, T, RAD...>::run(zsm, tb.Wp);
     // ---- pointwise product with the chirp spectrum (digit-reversed order on both sides)
     for (int idx = threadIdx.x; idx < S * M; idx += T) {
         const int s = idx / M, i = idx - s * M;
@@ -120,7 +134,7 @@ k_dct_bluestein(BluesteinTables tb, int P, int mode, DctPtrs ptrs, long ldx, int
         *p = cmul(*p, b);
     }
     __syncthreads();
-    DitPasses<M, M1, M, S, T, RAD...>::run(zsm, tb.W);
+    DitPasses<0, M, M1, M, S, T, RAD...>::run(zsm, tb.Wp);
 
     // ---- Z_k = conv_k conj(c_k); real split of the even extension; store
     const int half = (P + 1) / 2;                 // pairs (k, P-k), k = 0 .. half (k = 0 pairs with P)
@@ -174,6 +188,14 @@ static int launch_bluestein(const BluesteinTables &tb, int P, int mode, int njob
             return PDE_ERR_CUDA;
         }
         attr = true;
+    }
+    if (!tb.Wp) {
+        std::vector<double2> tab;
+        build_pass_tables<RAD...>(M, M, tab);
+        double2 *d = nullptr;
+        PDE_CUDA(cudaMalloc(&d, sizeof(double2) * tab.size()));
+        PDE_CUDA(cudaMemcpy(d, tab.data(), sizeof(double2) * tab.size(), cudaMemcpyHostToDevice));
+        const_cast<BluesteinTables &>(tb).Wp = d;
     }
     dim3 grid(ceil_div(batch, S), njobs);
     kern<<<grid, T, smem, st>>>(tb, P, mode, ptrs, ldx, n_in, ldy, n_out, batch);

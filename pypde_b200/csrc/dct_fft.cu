@@ -445,9 +445,10 @@ int fft_dct_exec(FftDctPlan *p, int mode, int njobs, const double *const *xs, lo
     }
     const int P = p->P;
     if (p->M) {
-        BluesteinTables tb{p->W, p->chirp, p->Bhat, p->CS};
+        BluesteinTables tb{p->W, p->chirp, p->Bhat, p->CS, p->Wp};
         const int rc = axis == 1 ? dispatch_bluestein<1>(p->M, tb, P, mode, njobs, ptrs, ldx, n_in, ldy, n_out, batch, st)
                                  : dispatch_bluestein<0>(p->M, tb, P, mode, njobs, ptrs, ldx, n_in, ldy, n_out, batch, st);
+        p->Wp = const_cast<double2 *>(tb.Wp);          // per-pass tables, built by the first launch
         if (rc < 0) {
             set_error("pde_dct1: no Bluestein kernel for M = %d", p->M);
             return PDE_ERR_UNSUPPORTED;
