@@ -264,8 +264,7 @@ def run_ensemble(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        quiet_nccl()
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        init_nccl(local)
     from pypde_b200 import _cabi
     from pypde_b200.navier.ensemble import Ensemble
     ra = np.logspace(4, 8, ENSEMBLE["members"])
@@ -341,6 +340,26 @@ def quiet_nccl():
         os.environ["NCCL_DEBUG"] = "WARN"
 
 
+def init_nccl(local):
+    """init_process_group + the first collective with file descriptor 1 pointed at stderr: whatever the NCCL
+    library prints while it creates the communicator (the version banner arrived on stdout even with
+    NCCL_DEBUG=WARN set here) must not land next to the ONE JSON line rank 0 prints."""
+    import torch
+    import torch.distributed as dist
+    quiet_nccl()
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 def run_gpu(args, cfg):
     import torch
     import torch.distributed as dist
@@ -351,8 +370,7 @@ def run_gpu(args, cfg):
     torch.cuda.set_device(local)
     slab = world > 1
     if slab:
-        quiet_nccl()
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        init_nccl(local)
         # Capturing the NCCL transposes in the CUDA graph works (rbc512 x2: 2.74 vs 3.03 ms/step) but the
         # process then hung in teardown on this stack, so the multi-GPU step is launched eagerly.
         if os.environ.get("PDE_SLAB_GRAPH", "0") != "1":
@@ -451,8 +469,8 @@ def run_gpu(args, cfg):
     roof_dct = {"kernel": "k_dct_fft (shared-memory FFT DCT-I, all batched transforms of the step)", "bound": "hbm",
                 "achieved": dct_work / (dct_ms * 1e-3) / 1e9 if dct_ms else None, "peak": peaks.get("hbm_gbs"),
                 "unit": "GB/s",
-                "traffic": 548850000,
-                "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the four DCT "
+                "traffic": 548850000 if (tuple(cfg["shape"]) == (2048, 2048) and not slab) else None,
+                "traffic_note": "(rbc2048 on one GPU only) dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the four DCT "
                                 "launches of one stage (ncu --set full of an eager rbc2048 stage, "
                                 "profiles/r01_ncu_stage_final.csv: 8 backward arrays along axis 0 634 MB, 8 backward "
                                 "along axis 1 982 MB, 3 forward along axis 1 352 MB, 3 forward along axis 0 227 MB) "
