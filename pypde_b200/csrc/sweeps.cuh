@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(BD) k_sweep(SweepJobs jobs)
             const int tl = Op::tab_len(k, n);
             for (int t = threadIdx.x; t < H; t += BD) {
                 const int i = par + 2 * t;
-                tsm[k * H + t] = (tp != nullptr && i < tl) ? __ldg(tp + i) : 0.0;
+                tsm[t * NT + k] = (tp != nullptr && i < tl) ? __ldg(tp + i) : 0.0;
             }
         }
         __syncwarp();
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(BD) k_sweep(SweepJobs jobs)
     typename Op::State st;
     Op::init(st, job, n, q);
     st.tsm = tsm;
-    st.H = H;
+    st.set_chunk(par);
     const int nchunks = (np + C - 1) / C;
     // chunks [c_lo, c_hi) are "interior": full, every stream index valid, no edge logic in Op::step
     // (all their steps satisfy 8 <= i <= n-9)
@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(BD) k_sweep(SweepJobs jobs)
         }
         if (c + SW_KC - 1 < nchunks) issue_chunk(c + SW_KC - 1);
         cp_async_commit_group();
+        st.set_chunk(Op::ASC ? par + 2 * c * C : top - 2 * c * C);
 #pragma unroll
         for (int e = 0; e < C; ++e) {
             const int t = c * C + e;
@@ -270,6 +271,7 @@ __global__ void __launch_bounds__(BD) k_sweep(SweepJobs jobs)
         prefetch_chunk(c + SW_KC - 1 + SW_PF);
         const int i0 = Op::ASC ? par + 2 * c * C : top - 2 * c * C;
         out.chunk(i0);
+        st.set_chunk(i0);
 #pragma unroll
         for (int e = 0; e < C; ++e) Op::template step<true>(st, job, n, Op::ASC ? i0 + 2 * e : i0 - 2 * e, v[e], out);
     };
@@ -303,13 +305,25 @@ __global__ void __launch_bounds__(BD) k_sweep(SweepJobs jobs)
 #define PDE_TB(st, k, i) ((st).tb((k), (i)))
 
 // Where an operator finds its per-index tables:
-//   TabParity (k_sweep):      the parity half this thread walks, staged per CTA: table k, index i -> tsm[k*H + (i >> 1)]
+//   TabParityT<NT> (k_sweep): the parity half this thread walks, staged per CTA: table k, index i -> tsm[(i >> 1)*NT + k]
 //   TabTile   (k_sweep_tile): the slice [i0 - 2, i0 + TW + 2) of every table, staged per tile:  tt[k*TTP + (i - i0) + 2]
-struct TabParity {
+template <int NT>
+struct TabParityT {
+    // entry (table k, index i) of the parity half this thread walks: tsm[(i >> 1) * NT + k] (the tables interleaved, so
+    // that one pointer per chunk -- pc, element `ibase` -- reaches every table entry of the chunk with a compile-time
+    // offset; the first layout, tsm[k * H + (i >> 1)] with run-time H, cost two integer instructions per table read:
+    // 14 IMAD + 5 LEA per step in the SASS of the 4-table back substitution)
     const double *tsm;
-    int H;
-    __device__ __forceinline__ double tb(int k, int i) const { return tsm[k * H + (i >> 1)]; }
+    const double *pc;
+    int ibase;
+    __device__ __forceinline__ void set_chunk(int i0)
+    {
+        ibase = i0;
+        pc = tsm + (i0 >> 1) * NT;
+    }
+    __device__ __forceinline__ double tb(int k, int i) const { return pc[((i - ibase) >> 1) * NT + k]; }
 };
+using TabParity = TabParityT<0>;
 constexpr int TILE_W = 64;               // elements of a sequence per tile
 constexpr int TILE_P = TILE_W + 2;       // row pitch of a tile in shared memory (33 x 16 bytes: odd, conflict-free)
 constexpr int TILE_TP = TILE_W + 4;      // table slice per tile
@@ -372,7 +386,7 @@ struct DiffDesc {
 // tdma.f90:55-106, k = 2, forward part: g_i = (rhs_i - a_{i-2} g_{i-2}) / den_i with the fused
 // S^T product rhs_i = u_i + s_i u_{i+2} (chebyshev.py:327) when tab[0] = s is given.
 // job.tab: 0 = s (or null), 1 = a, 2 = den, 3 = w (back substitution), 4 = RN(1/den) (optional).
-template <bool FULL, class TAB = TabParity>
+template <bool FULL, class TAB = TabParityT<4>>
 struct TdmaFwd {
     static constexpr int NIN = 2;
     static constexpr int NT = 4;          // staged: 0 = s, 1 = a, 2 = den, 3 = rden
@@ -415,7 +429,7 @@ struct TdmaFwd {
 };
 
 // back substitution x_i = g_i - w_i x_{i+2} (in place), job.tab[3] = w
-template <bool FULL, class TAB = TabParity>
+template <bool FULL, class TAB = TabParityT<1>>
 struct TdmaBwd {
     static constexpr int NIN = 1;
     static constexpr int NT = 1;
@@ -446,7 +460,7 @@ struct TdmaBwd {
 };
 
 // fdma.f90:26-36: forward x_i -= l_{i-2} x_{i-2}; job.tab: 0 = l, 1 = d, 2 = u1, 3 = u2, 4 = RN(1/d) (optional)
-template <bool FULL, class TAB = TabParity>
+template <bool FULL, class TAB = TabParityT<1>>
 struct FdmaFwd {
     static constexpr int NIN = 1;
     static constexpr int NT = 1;
@@ -476,7 +490,7 @@ struct FdmaFwd {
     }
 };
 
-template <bool FULL, class TAB = TabParity>
+template <bool FULL, class TAB = TabParityT<4>>
 struct FdmaBwd {
     static constexpr int NIN = 1;
     static constexpr int NT = 4;          // staged: 0 = d, 1 = u1, 2 = u2, 3 = rd
@@ -514,7 +528,7 @@ struct FdmaBwd {
 };
 
 // twodma.f90:17-22; job.tab: 0 = d, 1 = u, 4 = RN(1/d) (optional)
-template <bool FULL, class TAB = TabParity>
+template <bool FULL, class TAB = TabParityT<3>>
 struct TwodmaBwd {
     static constexpr int NIN = 1;
     static constexpr int NT = 3;          // staged: 0 = d, 1 = u, 2 = rd
@@ -552,7 +566,7 @@ struct TwodmaBwd {
 // Poisson (A + lam_q C) columns with per-column LU tables (n x m arrays, same layout as x):
 // streams: 0 = x, 1 = L (read at i-2);  itab[q] = 1 where the singular branch drops row/col 0
 // (fdma.f90:173-185): that column's system starts at i = 1 and x[0] = 0.
-template <bool FULL, class TAB = TabParity>
+template <bool FULL, class TAB = TabParityT<0>>
 struct PoissonFwd {
     static constexpr int NIN = 2;
     static constexpr int NT = 0;
@@ -587,7 +601,7 @@ struct PoissonFwd {
 };
 
 // streams: 0 = x, 1 = D, 2 = U1, 3 = U2, 4 = RN(1/D)
-template <bool FULL, class TAB = TabParity>
+template <bool FULL, class TAB = TabParityT<0>>
 struct PoissonBwd {
     static constexpr int NIN = 5;
     static constexpr int NT = 0;
