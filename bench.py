@@ -150,6 +150,11 @@ def run_reference(args, cfg):
     if rank != 0:
         return
     budget = float(os.environ.get("PDE_BENCH_CPU_BUDGET_S", "150"))
+    try:        # torchrun exports OMP_NUM_THREADS=1: give the two dense BLAS products all host cores back
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cpu_cores())
+    except Exception:
+        pass
     from oracle import pypde_port as P
     o = P.RBC2D(**cfg)
     init_state(o, cfg["shape"], port=True)
