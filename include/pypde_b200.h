@@ -164,7 +164,11 @@ typedef struct {
  *   TDMA_BWD    in[0] = g (usually == out), tab[3] = w
  *   FDMA_FWD    tab[0] = l;   FDMA_BWD  tab: 1 = d, 2 = u1, 3 = u2, 4 = RN(1/d) (optional)
  *   TWODMA_BWD  tab: 0 = d, 1 = u, 4 = RN(1/d) (optional)
- *   POISSON_*   driven by pde_poisson_solve (per-column tables as extra streams) */
+ *   POISSON_*   driven by pde_poisson_solve (per-column tables as extra streams)
+ * Kernel choice (results are bit-identical): axis-1 sweeps of even length >= 128 whose rows, pitches and
+ * tables are 16-byte aligned run tile by tile (32 rows per CTA, coalesced 512-byte row segments); TDMA_BWD /
+ * FDMA_FWD leave their first / last two indices unwritten, so the tiled form needs out == in[0] for them;
+ * DIFF with a power-of-two sc multiplies by RN(1/sc).  Everything else takes the generic row-per-lane kernel. */
 #define PDE_SWEEP_DIFF 0
 #define PDE_SWEEP_TDMA_FWD 1
 #define PDE_SWEEP_TDMA_BWD 2
