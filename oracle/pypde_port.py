@@ -655,3 +655,107 @@ class RBC2D:
     def state(self):
         return {"T": self.That_.copy(), "U": self.Uhat.copy(), "V": self.Vhat.copy(),
                 "P": self.Phat.copy(), "pres": self.pres.copy()}
+
+
+class RBC2DAdjoint:
+    """navier/rbc2d_adj.py:15-356 on NumPy arrays (TEST INFRASTRUCTURE, like everything in oracle/):
+    adjoint-descent iteration towards steady states.  Every stage (i) advances the forward model one step to
+    get the residual (state_new - state) / dt (:189-197), (ii) smooths it with three non-singular Poisson solves
+    into the adjoint fields (:199-205), (iii) updates U, V explicitly with the adjoint convective terms
+    (:207-262), projects them divergence free (:289-303, :341-349) and (iv) updates T (:264-287)."""
+
+    def __init__(self, **cfg):
+        self.NS = RBC2D(**cfg)
+        ns = self.NS
+        self.dt, self.scale, self.dealias = ns.dt, ns.scale, ns.dealias
+        self.nu, self.kappa = ns.nu, ns.kappa
+        self.sT, self.sU, self.sV, self.sP, self.deriv = ns.sT, ns.sU, ns.sV, ns.sP, ns.deriv
+        self.That_ = np.zeros(self.sT.shape_spectral)
+        self.Uhat = np.zeros(self.sU.shape_spectral)
+        self.Vhat = np.zeros(self.sV.shape_spectral)
+        self.Phat = np.zeros(self.sP.shape_spectral)
+        self.pres = np.zeros(ns.shape)
+        self.TA = np.zeros(self.sT.shape_spectral)
+        self.UA = np.zeros(self.sU.shape_spectral)
+        self.VA = np.zeros(self.sV.shape_spectral)
+        # rbc2d_adj.py:133-150
+        self.a, self.b, self.c, self.nstage = ns.a, ns.b, ns.c, ns.nstage
+        self.solver_P = ns.solver_P
+        self.nabla_U = PoissonEig(self.sU.xs, singular=False, scale=self.scale)
+        self.nabla_V = PoissonEig(self.sV.xs, singular=False, scale=self.scale)
+        self.nabla_T = PoissonEig(self.sT.xs, singular=False, scale=self.scale)
+        # rbc2d_adj.py:112-117: the lifting temperature in physical space
+        dsp = self.deriv.dealias if self.dealias else self.deriv
+        self.temp_bc = dsp.backward(ns.sTbc.to_cheb(ns.Tbc_vhat))
+        self.time = 0.0
+
+    def _phys(self, space, vhat):
+        return (space.dealias if self.dealias else space).backward(vhat)
+
+    def _conv(self, space, vhat, u, deriv):
+        """field_operations.py:83-129: u * d(field)/dx_i in physical space"""
+        dsp = self.deriv.dealias if self.dealias else self.deriv
+        return dsp.backward(space.grad(vhat, deriv, self.scale)) * u
+
+    def _conv_adj(self, deriv, ux, uz, temp):
+        """rbc2d_adj.py:162-187"""
+        conv = self._conv(self.sU, self.UA, ux, deriv)
+        conv += self._conv(self.sV, self.VA, uz, deriv)
+        conv += self._conv(self.sT, self.TA, temp, deriv)
+        conv += self._conv(self.sT, self.TA, self.temp_bc, deriv)
+        return (self.deriv.dealias if self.dealias else self.deriv).forward(conv)
+
+    def _residual(self):
+        """rbc2d_adj.py:189-205"""
+        ns = self.NS
+        ns.Uhat[:], ns.Vhat[:], ns.That_[:] = self.Uhat, self.Vhat, self.That_
+        ns.update()
+        ns.Uhat[:] = (ns.Uhat - self.Uhat) / self.dt
+        ns.Vhat[:] = (ns.Vhat - self.Vhat) / self.dt
+        ns.That_[:] = (ns.That_ - self.That_) / self.dt
+        for plan, space, res, out, coef in ((self.nabla_U, self.sU, ns.Uhat, self.UA, self.nu),
+                                            (self.nabla_V, self.sV, ns.Vhat, self.VA, self.nu),
+                                            (self.nabla_T, self.sT, ns.That_, self.TA, self.kappa)):
+            out[:] = plan.solve_lhs(plan.solve_rhs(space.to_cheb(res))) / coef
+
+    def update(self):
+        """rbc2d_adj.py:321-356"""
+        ns, a, b, c = self.NS, self.a, self.b, self.c
+        ux_old = uz_old = temp_old = 0
+        for rk in range(self.nstage):
+            ux, uz, temp = self._phys(self.sU, self.Uhat), self._phys(self.sV, self.Vhat), self._phys(self.sT, self.That_)
+            self._residual()
+            for deriv, space, adj, res, state in (((1, 0), self.sU, self.UA, ns.Uhat, self.Uhat),
+                                                  ((0, 1), self.sV, self.VA, ns.Vhat, self.Vhat)):
+                rhs = np.zeros(ns.shape)
+                rhs -= a[rk] * self.deriv.grad(self.pres, deriv, self.scale)
+                rhs += b[rk] * ns.conv_term(space, adj, ux, uz)
+                rhs += b[rk] * self._conv_adj(deriv, ux, uz, temp)
+                if c[rk] != 0:
+                    rhs += c[rk] * ns.conv_term(space, adj, ux_old, uz_old)
+                    rhs += c[rk] * self._conv_adj(deriv, ux_old, uz_old, temp_old)
+                rhs += a[rk] * space.to_cheb(res)
+                state += self.dt * space.from_cheb(rhs)
+            # pressure projection (rbc2d_adj.py:289-303 with the forward model's divergence, rbc2d.py:225-234)
+            div = self.sU.grad(self.Uhat, (1, 0), self.scale) + self.sV.grad(self.Vhat, (0, 1), self.scale)
+            self.Phat[:] = self.solver_P.solve_lhs(self.solver_P.solve_rhs(div))
+            self.Phat[0, 0] = 0
+            self.pres += self.sP.to_cheb(self.Phat) / (self.dt * a[rk])
+            dpdx = self.sP.grad(self.Phat, (1, 0), self.scale)
+            dpdz = self.sP.grad(self.Phat, (0, 1), self.scale)
+            self.Uhat -= self.sU.from_cheb(dpdx * 1.0)
+            self.Vhat -= self.sV.from_cheb(dpdz * 1.0)
+            # temperature (rbc2d_adj.py:264-287)
+            rhs = np.zeros(ns.shape)
+            rhs += b[rk] * ns.conv_term(self.sT, self.TA, ux, uz)
+            if c[rk] != 0:
+                rhs += c[rk] * ns.conv_term(self.sT, self.TA, ux_old, uz_old)
+            rhs += a[rk] * self.sT.to_cheb(ns.That_)
+            rhs += a[rk] * self.sV.to_cheb(self.VA)
+            self.That_ += self.dt * self.sT.from_cheb(rhs)
+            ux_old, uz_old, temp_old = ux, uz, temp
+        self.time += self.dt
+
+    def state(self):
+        return {"T": self.That_.copy(), "U": self.Uhat.copy(), "V": self.Vhat.copy(), "P": self.Phat.copy(),
+                "pres": self.pres.copy(), "TA": self.TA.copy(), "UA": self.UA.copy(), "VA": self.VA.copy()}

@@ -1,2 +1,3 @@
 from . import rbc2d
 from .rbc2d import NavierStokes
+from .rbc2d_adj import NavierStokesAdjoint

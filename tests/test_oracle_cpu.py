@@ -158,3 +158,37 @@ def test_diffusion_port_matches_reference(name, cfg, snaps):
             step += 1
         assert rel_l2(o.vhat, g["%s_vhat_%d" % (name, s)]) < 1e-12, s
     assert rel_l2(o.total(), g[name + "_total"]) < 1e-12
+
+
+# name -> (config, forward steps before the adjoint iteration starts, snapshots): tests/golden/make_golden_adjoint.py
+ADJOINT_CASES = {
+    "adj32_eu": (dict(shape=(32, 32), dt=0.05, tsave=None, ra=5e3, pr=1.0, dealias=True, integrator="eu", beta=1.0),
+                 5, (1, 4)),
+    "adj24x32_rk3_aspect2": (dict(shape=(24, 32), dt=0.02, tsave=None, ra=1e4, pr=0.7, dealias=True,
+                                  integrator="rk3", beta=1.0, aspect=2.0), 5, (1, 3)),
+    "adj32_rk3_nodealias": (dict(shape=(32, 32), dt=0.05, tsave=None, ra=5e3, pr=1.0, dealias=False,
+                                 integrator="rk3", beta=1.0), 3, (1, 3)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(ADJOINT_CASES))
+def test_adjoint_port_matches_reference(name):
+    """oracle RBC2DAdjoint against the states of the unmodified reference navier/rbc2d_adj.py
+    (tests/golden/make_golden_adjoint.py; bit for bit there, <= 1e-12 here: the Poisson setup is host dependent)."""
+    g = load_golden("adjoint")
+    cfg, pre, snaps = ADJOINT_CASES[name]
+    o = P.RBC2DAdjoint(**cfg)
+    o.NS.set_temperature(amplitude=0.2)          # like the reference's __main__: pre-iterate the forward model,
+    for _ in range(pre):                         # hand its state (and its pressure history) to the adjoint iteration
+        o.NS.update()
+    o.That_[:], o.Uhat[:], o.Vhat[:] = o.NS.That_, o.NS.Uhat, o.NS.Vhat
+    for key, arr in (("T", o.That_), ("U", o.Uhat), ("V", o.Vhat)):
+        assert rel_l2(arr, g["%s_init_%s" % (name, key)]) < 1e-12, key
+    step = 0
+    for s in snaps:
+        while step < s:
+            o.update()
+            step += 1
+        st = o.state()
+        for key in ("T", "U", "V", "pres", "TA", "UA", "VA"):
+            assert rel_l2(st[key], g["%s_%s_%d" % (name, key, s)]) < 1e-12, (key, s)
