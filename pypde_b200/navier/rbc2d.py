@@ -19,14 +19,14 @@ from ..bases.spectralbase import Base, dealias_policy
 from ..field import Field, FieldBC, MultiField
 from ..field_operations import cheby_to_galerkin, convective_term, galerkin_to_cheby
 from ..solver.integrator import Integrator
-from .rbc2d_base import NavierStokesBase
+from .rbc2d_base import NavierStokesBase, NavierStokesSteadyState
 
 # wall-clock accumulators of the reference (navier/rbc2d.py:16-25); kept as names, the
 # meaningful timings are CUDA events in bench.py
 TIME = TIME_U = TIME_V = TIME_P = TIME_T = TIME_Update = TIME_Divergence = TIME_FFT = TIME_Conv = 0
 
 
-class NavierStokes(NavierStokesBase, Integrator):
+class NavierStokes(NavierStokesBase, NavierStokesSteadyState, Integrator):
     """
     rbc:    adiabatic side walls
     linear: isothermal side walls, linear temperature profile

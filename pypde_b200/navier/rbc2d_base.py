@@ -1,8 +1,8 @@
 """
 Configuration, non-dimensional parameters, time-step coefficients and Nusselt
 diagnostics of the Rayleigh-Benard solver (navier/rbc2d_base.py:8-257, :344-386).
-The steady-state and stability add-ons of the reference (:260-341, :389-452) are
-host-side SciPy drivers around update() and are outside the time-step path.
+The steady-state add-on (:260-341) is provided as a host-side SciPy Newton-Krylov driver around the device
+update(); the stability add-on (:389-452, dense eigenproblems of pypde/stability) is outside the time-step path.
 """
 import numpy as np
 import torch
@@ -136,6 +136,59 @@ class NavierStokesBase:
 
     def save(self):
         self.field.save()
+
+
+
+class NavierStokesSteadyState:
+    """Steady states by Newton-Krylov (rbc2d_base.py:260-341): SciPy's `optimize.root(method="krylov")` runs on
+    the host and drives the device time step.  The unknown is the flat vector [T, U, V] of Galerkin
+    coefficients; one residual evaluation uploads it into the fields, advances them (one step, or `dt` time
+    units) on the GPU and returns (new - old) / dt."""
+
+    def solve_steady_state(self, X0=None, dt=None, maxiter=300, disp=True, tol=1e-8, jac_options=None):
+        from scipy import optimize
+
+        if jac_options is None:
+            jac_options = {"inner_maxiter": 30}
+        if disp:
+            print("\nSolve steady state ...\n")
+        options = {"maxiter": maxiter, "disp": disp, "fatol": tol, "jac_options": jac_options}
+        if X0 is None:
+            X0 = self.vectorify()
+        return optimize.root(self.steady_fun, X0, args=(self, dt), method="krylov", options=options)
+
+    def _state_fields(self):
+        return (self.T, self.U, self.V)
+
+    def flatten(self):
+        return tuple(f.vhat.detach().cpu().numpy().ravel().copy() for f in self._state_fields())
+
+    def vectorify(self):
+        return np.concatenate(self.flatten())
+
+    def get_masks(self):
+        masks, pos = [], 0
+        for f in self._state_fields():
+            n = f.vhat.numel()
+            masks.append(slice(pos, pos + n))
+            pos += n
+        return tuple(masks)
+
+    def reshape(self, X):
+        return tuple(np.array(X[m]).reshape(tuple(f.vhat.shape)) for m, f in zip(self.get_masks(), self._state_fields()))
+
+    def steady_fun(self, X, NS, dt):
+        """X: flat [T, U, V] -> residual (NS(X) - X) / dt, flat, on the host."""
+        for f, part in zip(NS._state_fields(), NS.reshape(X)):
+            f.vhat[:] = torch.as_tensor(part, dtype=f.vhat.dtype, device=f.vhat.device)
+        if dt is None:
+            dt = NS.dt
+            NS.update()
+        else:
+            NS.reset_time()
+            NS.iterate(dt, callback=False)
+            NS.reset_time()
+        return (NS.vectorify() - X) / dt
 
 
 def _plate_gradient(T, field, Lz, Tbc):
