@@ -178,3 +178,23 @@ print("ok")
 ''' % (op, axis)
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, (r.returncode, r.stdout[-500:], r.stderr[-2000:])
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the reference's CPU path = the oracle port; runs without a GPU): ONE JSON line on
+    stdout with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, PDE_BENCH_CPU_BUDGET_S="5")
+    r = subprocess.run([sys.executable, "bench.py", "--impl", "reference", "--workload", "rbc64", "--steps", "2",
+                        "--warmup", "1"], cwd=ROOT, capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "rbc2d_fp64_timesteps_per_sec" and d["unit"] == "steps/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] >= 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"] == "rbc64"
