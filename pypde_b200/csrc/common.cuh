@@ -48,6 +48,26 @@ inline int after_launch(const char *what)
 
 int sm_count();
 
+// "done once" flags for per-device state (cudaFuncSetAttribute applies to the current device only)
+struct PerDeviceFlag {
+    bool done[64] = {};
+    bool &get()
+    {
+        int d = 0;
+        cudaGetDevice(&d);
+        return done[d & 63];
+    }
+};
+struct PerDeviceSize {
+    size_t v[64] = {};
+    size_t &get()
+    {
+        int d = 0;
+        cudaGetDevice(&d);
+        return v[d & 63];
+    }
+};
+
 inline int ceil_div(long a, long b) { return (int)((a + b - 1) / b); }
 
 #ifdef __CUDACC__

@@ -180,14 +180,14 @@ static int launch_bluestein(const BluesteinTables &tb, int P, int mode, int njob
     auto kern = k_dct_bluestein<M, S, T, AXIS, RAD...>;
     constexpr int M1 = M / FirstRadix<RAD...>::value;
     constexpr size_t smem = (size_t)S * Pad<M, M1>::SEQ * 16;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceFlag attr;
+    if (!attr.get()) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(k_dct_bluestein): %s", cudaGetErrorString(e));
             return PDE_ERR_CUDA;
         }
-        attr = true;
+        attr.get() = true;
     }
     if (!tb.Wp) {
         std::vector<double2> tab;

@@ -413,11 +413,11 @@ int fft_dct_create(FftDctPlan **out, int L)
     PDE_CUDA(cudaMemcpy(p->W, W.data(), sizeof(double2) * P, cudaMemcpyHostToDevice));
     PDE_CUDA(cudaMemcpy(p->CS, CS.data(), sizeof(double2) * (P / 2 + 1), cudaMemcpyHostToDevice));
     PDE_CUDA(cudaMemcpy(p->pos, pos.data(), sizeof(int) * P, cudaMemcpyHostToDevice));
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceFlag attr;
+    if (!attr.get()) {
         PDE_CUDA(cudaFuncSetAttribute(k_dct_fft<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
         PDE_CUDA(cudaFuncSetAttribute(k_dct_fft<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024));
-        attr = true;
+        attr.get() = true;
     }
     *out = p;
     return PDE_OK;

@@ -508,8 +508,8 @@ static int launch_fft_t(const FftDctPlan *p, int mode, int njobs, const DctPtrs 
         PDE_CUDA(cudaMemcpy(d, tab.data(), sizeof(double2) * tab.size(), cudaMemcpyHostToDevice));
         const_cast<FftDctPlan *>(p)->Wp = d;
     }
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceFlag attr;
+    if (!attr.get()) {
         // Shared-memory carve-out: room for up to 3 CTAs, and never more than needed -- what is left of the
         // 256 KB is L1, which has to hold the twiddle tables (16 P bytes).  The S = 4 axis-0 CTAs need
         // 193 KB + 1 KB: asking for 100 % left a 28 KB L1 that thrashed (0.31 ms); the 196 KB configuration
@@ -525,7 +525,7 @@ static int launch_fft_t(const FftDctPlan *p, int mode, int njobs, const DctPtrs 
             set_error("cudaFuncSetAttribute(k_dct_fft_t): %s", cudaGetErrorString(e));
             return PDE_ERR_CUDA;
         }
-        attr = true;
+        attr.get() = true;
     }
     // (Tried: launching the axis-0 CTAs as clusters of 2/4/8 so that the four 32-byte sectors of a line are
     // requested close in time, and other shared-memory carve-outs: no effect once the row pitch of the arrays

@@ -193,10 +193,10 @@ static int gemm_launch(const double *A, long lda, const double *B, long ldb, dou
                        int k, cudaStream_t st)
 {
     auto kern = k_gemm_f64<TB, VEC, MI, NI, WN>;
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceFlag attr;
+    if (!attr.get()) {
         PDE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-        attr = true;
+        attr.get() = true;
     }
     constexpr int BM = (8 / WN) * 8 * MI, BNT = WN * 8 * NI;
     dim3 grid(ceil_div(n, BNT), ceil_div(m, BM));

@@ -829,10 +829,10 @@ static int launch_sweep_tile(const SweepJobs &jobs, cudaStream_t st, const char 
     for (int j = 0; j < jobs.njobs; ++j) maxseq = jobs.j[j].nseq > maxseq ? jobs.j[j].nseq : maxseq;
     if (maxseq <= 0) return PDE_OK;
     const size_t smem = ((size_t)NST * TileStage<Op>::value + 32 * TILE_P) * sizeof(double);
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceFlag attr;
+    if (!attr.get()) {
         PDE_CUDA(cudaFuncSetAttribute(k_sweep_tile<Op, NST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
+        attr.get() = true;
     }
     dim3 grid(ceil_div(maxseq, 32), jobs.njobs);
     k_sweep_tile<Op, NST><<<grid, 64, smem, st>>>(jobs);
@@ -854,7 +854,8 @@ static int launch_sweep(const SweepJobs &jobs, int axis, cudaStream_t st, const 
         set_error("%s: sequence length %d needs %zu bytes of shared memory", what, jobs.n, smem);
         return PDE_ERR_UNSUPPORTED;
     }
-    static size_t attr_lc = 0, attr_ts = 0;
+    static PerDeviceSize attr_lc_, attr_ts_;
+    size_t &attr_lc = attr_lc_.get(), &attr_ts = attr_ts_.get();
     if (axis == 0) {
         if (smem > 48 * 1024 && smem > attr_lc) {
             PDE_CUDA(cudaFuncSetAttribute(k_sweep<Op, true, BD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

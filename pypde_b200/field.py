@@ -112,8 +112,21 @@ class FieldBase:
         grp = grp_name + "/" if grp_name and grp_name[-1] != "/" else grp_name
         print("Read {:s} ...".format(filename))
         data = _npz_load(filename)
-        self.v = data[grp + "v"]
-        self.vhat = data[grp + "vhat"]
+        if not data:
+            raise FileNotFoundError(
+                "%s: no checkpoint found (this build stores the reference's HDF5 layout as %s because h5py is "
+                "not part of the image; HDF5 files written by pypde cannot be read here)" % (filename, _npz_name(filename)))
+        for key in (grp + "v", grp + "vhat", "time"):
+            if key not in data:
+                raise KeyError("%s: dataset %r missing from checkpoint" % (_npz_name(filename), key))
+        # in place, like the reference (`self.vhat[:] = ...`, field.py:150-152): a checkpoint of another
+        # resolution is an error, and tensors bound into launch lists / CUDA graphs stay valid
+        for name, arr in (("v", data[grp + "v"]), ("vhat", data[grp + "vhat"])):
+            cur = getattr(self, name)
+            if tuple(arr.shape) != tuple(cur.shape):
+                raise ValueError("%s: checkpoint %s has shape %s, field expects %s"
+                                 % (_npz_name(filename), grp + name, tuple(arr.shape), tuple(cur.shape)))
+            cur.copy_(C.to_dev(arr))
         self.t = float(data["time"])
         if dict is not None:
             for key in dict:

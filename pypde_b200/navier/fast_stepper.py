@@ -86,8 +86,10 @@ class FastStepper:
         self.g3 = [self._new(N0, N1) for _ in range(3)]       # dz(e)/sz
         self.thc = self._new(N0, N1)
         self.X8 = [self._new(D0, N1) for _ in range(8)]
-        self.phys = [self._new(D0, D1) for _ in range(6)]     # dxU dxV dxT dzU dzV dzT
-        self.uw = [[self._new(D0, D1), self._new(D0, D1)] for _ in range(2)]
+        # pde_conv_products indexes its 13 arrays flat over D0*D1: these stay contiguous (no pitch padding)
+        flat = lambda: torch.zeros((D0, D1), dtype=torch.float64, device=self.dev)
+        self.phys = [flat() for _ in range(6)]                # dxU dxV dxT dzU dzV dzT
+        self.uw = [[flat(), flat()] for _ in range(2)]
         self.F3 = [self._new(D0, N1) for _ in range(3)]
         self.conv = [self._new(N0, N1) for _ in range(3)]
         self.dpdx, self.dpdz = self._new(N0, N1), self._new(N0, N1)
@@ -254,6 +256,8 @@ class FastStepper:
         self._dct(calls, self.plan1, ops.BWD, 1, self.X8, dst)
         # -- products (both convective terms of the stage merged: ub = b u + c u_old)
         use_old = c != 0.0
+        for t in list(new) + list(old) + list(self.phys) + [self.dTbcdz1]:
+            assert t.is_contiguous() and tuple(t.shape) == (self.D0, self.D1)
         calls.add(L.pde_conv_products, self.D0 * self.D1, b, c, _ptr(new[0]), _ptr(new[1]),
                   _ptr(old[0]) if use_old else None, _ptr(old[1]) if use_old else None,
                   _ptr(dxU), _ptr(dzU), _ptr(dxV), _ptr(dzV), _ptr(dxT), _ptr(dzT), _ptr(self.dTbcdz1))

@@ -111,6 +111,8 @@ class NavierStokes(NavierStokesBase, NavierStokesSteadyState, Integrator):
         space = self.deriv_field.dealias if self.dealias else self.deriv_field
         self.dTbcdz1 = space.backward(vhat)
         self.Tbc_cheby = galerkin_to_cheby(self.Tbc.vhat, self.Tbc)
+        self._fast = None          # the batched stepper snapshots Tbc_cheby / dTbcdz1 / dTbcdz2
+        self._graph = None
 
     def set_temp_fieldbc_linear(self):
         bc = np.zeros((self.shape[0], 2))
@@ -231,6 +233,17 @@ class NavierStokes(NavierStokesBase, NavierStokesSteadyState, Integrator):
         else:
             self._update_graph()
         self.ux, self.uz = self._fast.ux, self._fast.uz
+
+    # -- parts of the reference class that are outside the time-step path (out of scope) ------
+    def solve_stability(self, *args, **kwargs):
+        raise NotImplementedError("NavierStokesStability (navier/rbc2d_base.py:389-452: dense host eigenproblems of "
+                                  "pypde/stability) is not part of pypde_b200")
+
+    def plot(self, *args, **kwargs):
+        raise NotImplementedError("plotting (pypde/plot) is not part of pypde_b200; use field.v.cpu().numpy()")
+
+    def animate(self, *args, **kwargs):
+        raise NotImplementedError("plotting (pypde/plot) is not part of pypde_b200; use field.V after save()")
 
     def sync_fields(self):
         """Slab mode: gather the distributed state into T, U, V, pres of every rank."""

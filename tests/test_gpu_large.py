@@ -1,0 +1,258 @@
+"""GPU parity of the time step on the configurations BASELINE.json names (configs[3]: rbc2d 512x512, Ra = 1e8;
+configs[4]: rbc2d 2048x2048, Ra = 1e10) and on the code paths that only exist at large sizes
+(row-pitch padding, tiled / chain-split sweeps, the P = 768 / 3072 FFT specialisations, Bluestein at 3072,
+the wave-filling GEMM tiles): CUDA path against the CPU oracle (oracle/pypde_port.py, bit-identical to
+the unmodified reference: tests/golden/make_golden.py) run on THIS host from the same seeded state
+(reference: navier/rbc2d.py:396-434).  Tolerance of the north star: <= 1e-12 relative L2 per coefficient array.
+
+The measured errors are appended to gpurun_out/parity_large.json (copied to profiles/ as evidence).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, rel_l2
+from test_gpu_rbc import H, make, make_oracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _record(key, value):
+    path = os.path.join(ROOT, "gpurun_out", "parity_large.json")
+    try:
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        data = json.load(open(path)) if os.path.exists(path) else {}
+        data[key] = value
+        json.dump(data, open(path, "w"), indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def _state_errors(ns, o):
+    return {k: rel_l2(H(t), r) for k, t, r in (("T", ns.T.vhat, o.That_), ("U", ns.U.vhat, o.Uhat),
+                                               ("V", ns.V.vhat, o.Vhat), ("pres", ns.pres.vhat, o.pres))}
+
+
+def _cfg(n, ra, dt, **kw):
+    cfg = dict(case="rbc", shape=(n, n), ra=ra, pr=1.0, dt=dt, tsave=None, dealias=True, integrator="rk3",
+               beta=1.0, aspect=1.0)
+    cfg.update(kw)
+    return cfg
+
+
+def test_rbc512_three_steps_vs_oracle():
+    """configs[3]: 3 RK3 steps at 512x512, Ra = 1e8."""
+    cfg = _cfg(512, 1e8, 1e-3)
+    ns, o = make(cfg), make_oracle(cfg)
+    for step in (1, 2, 3):
+        ns.update()
+        o.update()
+        err = _state_errors(ns, o)
+        _record("rbc512_step%d" % step, err)
+        for k, e in err.items():
+            assert e < TOL, "rbc512 step %d %s: CUDA vs oracle rel L2 %.3e" % (step, k, e)
+
+
+def test_rbc2048_one_step_vs_oracle_and_stepper_agreement():
+    """configs[4] (the bench workload): one RK3 step at 2048x2048, Ra = 1e10 against the oracle; then 10 steps of
+    the batched stepper against the operator-by-operator stepper (the reference's order) and against the
+    reference's own dealias grid (3072 points instead of the FFT-friendly 3073)."""
+    import torch
+    cfg = _cfg(2048, 1e10, 1e-4)
+    ns, o = make(cfg), make_oracle(cfg)
+    ns.update()
+    o.update()
+    err = _state_errors(ns, o)
+    _record("rbc2048_step1", err)
+    for k, e in err.items():
+        assert e < TOL, "rbc2048 step 1 %s: CUDA vs oracle rel L2 %.3e" % (k, e)
+    del o
+    ref = make(cfg, stepper="reference")
+    grid = make(cfg, dealias_grid="reference")
+    assert tuple(ns.U.dealias.shape_physical) == (3073, 3073) and tuple(grid.U.dealias.shape_physical) == (3072, 3072)
+    ref.update()
+    grid.update()
+    for _ in range(9):
+        ns.update()
+        ref.update()
+        grid.update()
+    torch.cuda.synchronize()
+    for other, tag in ((ref, "reference_stepper"), (grid, "reference_grid")):
+        e10 = {k: rel_l2(H(a), H(b)) for k, a, b in (("T", ns.T.vhat, other.T.vhat), ("U", ns.U.vhat, other.U.vhat),
+                                                     ("V", ns.V.vhat, other.V.vhat),
+                                                     ("pres", ns.pres.vhat, other.pres.vhat))}
+        _record("rbc2048_step10_vs_" + tag, e10)
+        for k, e in e10.items():
+            assert e < TOL, "rbc2048 10 steps, batched vs %s, %s: %.3e" % (tag, k, e)
+
+
+@pytest.mark.parametrize("shape,kw", [
+    ((256, 256), dict(dealias=False)),                       # D1 = 256: pitch-padded physical arrays
+    ((512, 512), dict(dealias_grid="reference")),            # D1 = 768
+    ((256, 384), dict(dealias=False, integrator="eu")),      # rectangular, both pitches padded
+])
+def test_pitch_padded_grids_vs_oracle(shape, kw):
+    """Physical grids whose width is a multiple of 256 (work arrays get a padded row pitch)."""
+    kw = dict(kw)
+    grid = kw.pop("dealias_grid", "fft")
+    cfg = dict(case="rbc", shape=shape, ra=1e7, pr=1.0, dt=2e-3, tsave=None, dealias=True, integrator="rk3",
+               beta=1.0, aspect=1.0)
+    cfg.update(kw)
+    ns, o = make(cfg, dealias_grid=grid), make_oracle(cfg)
+    for _ in range(2):
+        ns.update()
+        o.update()
+    err = _state_errors(ns, o)
+    _record("pitch_%dx%d_%s" % (shape[0], shape[1], grid), err)
+    for k, e in err.items():
+        assert e < TOL, (shape, kw, k, e)
+
+
+@pytest.mark.parametrize("n,dealias", [(64, False), (96, False), (256, False)])
+def test_convective_term_vs_oracle(n, dealias):
+    """conv_term / convective_term (pypde/field_operations.py:83-169) and the fused product kernel
+    pde_conv_products directly against the oracle's RBC2D.conv_term."""
+    import ctypes
+    import torch
+    from pypde_b200 import _cabi as C
+    cfg = dict(case="rbc", shape=(n, n), ra=1e6, pr=1.0, dt=1e-3, tsave=None, dealias=dealias, integrator="rk3",
+               beta=1.0, aspect=1.0)
+    ns, o = make(cfg), make_oracle(cfg)
+    ns.update()
+    o.update()
+    # start both from the oracle's state so that only the operator under test differs
+    for f, a in ((ns.T, o.That_), (ns.U, o.Uhat), (ns.V, o.Vhat)):
+        f.vhat.copy_(torch.as_tensor(a, device=f.vhat.device))
+    dsp_o = o.sU.dealias if dealias else o.sU
+    ux_o, uz_o = dsp_o.backward(o.Uhat), (o.sV.dealias if dealias else o.sV).backward(o.Vhat)
+    ux = (ns.U.dealias if dealias else ns.U).backward(ns.U.vhat)
+    uz = (ns.V.dealias if dealias else ns.V).backward(ns.V.vhat)
+    if tuple(ux.shape) != ux_o.shape:
+        pytest.skip("FFT-friendly dealias grid differs from the oracle's (physical arrays not comparable)")
+    assert rel_l2(H(ux), ux_o) < 1e-13
+    for f, sp, vhat, bc in ((ns.U, o.sU, o.Uhat, None), (ns.T, o.sT, o.That_, True)):
+        add_o = uz_o * o.dTbcdz1 if bc else None
+        add = uz * ns.dTbcdz1 if bc else None
+        got = ns.conv_term(f, ux, uz, add_bc=add)
+        want = o.conv_term(sp, vhat, ux_o, uz_o, add_bc=add_o)
+        assert rel_l2(H(got), want) < 1e-13, rel_l2(H(got), want)
+    # fused products: dxU <- (b u + c u_old) dxU + (b w + c w_old) dzU, ... on contiguous arrays
+    rng = np.random.default_rng(5)
+    D = tuple(ux.shape)
+    hs = [rng.standard_normal(D) for _ in range(11)]
+    u, w, uo, wo, dxU, dzU, dxV, dzV, dxT, dzT, dTbc = [torch.as_tensor(h, device=ux.device).contiguous() for h in hs]
+    b, c = 5.0 / 12.0, -17.0 / 60.0
+    C.check(C.lib().pde_conv_products(D[0] * D[1], b, c, C.p(u), C.p(w), C.p(uo), C.p(wo), C.p(dxU), C.p(dzU),
+                                      C.p(dxV), C.p(dzV), C.p(dxT), C.p(dzT), C.p(dTbc), C.stream()))
+    ub, wb = b * hs[0] + c * hs[2], b * hs[1] + c * hs[3]
+    for got, want in ((dxU, ub * hs[4] + wb * hs[5]), (dxV, ub * hs[6] + wb * hs[7]),
+                      (dxT, ub * hs[8] + wb * hs[9] + wb * hs[10])):
+        assert rel_l2(H(got), want) < 1e-14
+
+
+def test_convective_term_reference_grid_vs_oracle():
+    """Same with dealias_grid="reference" so that the physical arrays are comparable point by point."""
+    import torch
+    n = 64
+    cfg = dict(case="rbc", shape=(n, n), ra=1e6, pr=1.0, dt=1e-3, tsave=None, dealias=True, integrator="rk3",
+               beta=1.0, aspect=1.0)
+    ns, o = make(cfg, dealias_grid="reference"), make_oracle(cfg)
+    ux_o, uz_o = o.sU.dealias.backward(o.Uhat), o.sV.dealias.backward(o.Vhat)
+    ux, uz = ns.U.dealias.backward(ns.U.vhat), ns.V.dealias.backward(ns.V.vhat)
+    assert tuple(ux.shape) == ux_o.shape == (96, 96)
+    assert rel_l2(H(ux), ux_o) < 1e-13 and rel_l2(H(uz), uz_o) < 1e-13
+    got = ns.conv_term(ns.T, ux, uz, add_bc=uz * ns.dTbcdz1)
+    want = o.conv_term(o.sT, o.That_, ux_o, uz_o, add_bc=uz_o * o.dTbcdz1)
+    assert rel_l2(H(got), want) < 1e-13
+
+
+def test_nusselt_noise_floor_and_error():
+    """Nu after 100 steps at 64x64 (north star: <= 1e-12) with the evidence for what the diagnostic resolves.
+
+    eval_Nu (navier/rbc2d_base.py:344-363) differentiates at the wall after a physical-space round trip.
+    The ORACLE's own value moves by `floor` when its input coefficients are perturbed by half an ulp
+    (1e-16 relative: most entries do not change at all): that is the resolution of the reference's
+    diagnostic at this N, measured here (lower bounds asserted), and the CUDA value is required to agree to
+    max(1e-12, 8 floor).  The numbers are written to gpurun_out/parity_large.json."""
+    import contextlib
+    import io
+    from test_oracle_cpu import _cases
+    out = {}
+    for name, nsteps, lower in (("rbc64_rk3_dealias", 100, 2e-14), ("rbc128_rk3_dealias", 10, 1e-13)):
+        cfg = _cases()[name]
+        ns, o = make(cfg), make_oracle(cfg)
+        for _ in range(nsteps):
+            ns.update()
+            o.update()
+        nu_o = o.eval_Nu()
+        T0 = o.That_.copy()
+        floor = 0.0
+        for seed in range(8):
+            o.That_ = T0 * (1.0 + 1e-16 * np.random.default_rng(seed).standard_normal(T0.shape))
+            floor = max(floor, abs(o.eval_Nu()[0] - nu_o[0]) / abs(nu_o[0]))
+        o.That_ = T0
+        with contextlib.redirect_stdout(io.StringIO()):
+            nu, nuv = ns.eval_Nu()
+        err = abs(nu - nu_o[0]) / abs(nu_o[0])
+        errv = abs(nuv - nu_o[1]) / max(1.0, abs(nu_o[1]))
+        state = _state_errors(ns, o)
+        out[name] = dict(steps=nsteps, nu_oracle=nu_o[0], nu_cuda=nu, rel_err_nu=err, rel_err_nuvol=errv,
+                         oracle_half_ulp_noise_floor=floor, state_rel_l2=state)
+        _record("nusselt_" + name, out[name])
+        assert floor > lower, "the oracle's Nu is better conditioned than claimed: %.3e" % floor
+        assert err <= max(TOL, 8 * floor), (name, err, floor)
+        assert errv <= max(TOL, 8 * floor), (name, errv, floor)
+        for k, e in state.items():
+            assert e < TOL, (name, k, e)
+
+
+def test_checkpoint_roundtrip_and_interpolate(tmp_path):
+    """Field / MultiField write -> read (pypde/field.py:83-173,440-459; same keys as the HDF5 layout) and
+    interpolate (field_operations.py:184-220) 64 -> 96 -> 64 against the oracle's arrays."""
+    import torch
+    from pypde_b200.navier import rbc2d
+    from test_oracle_cpu import _cases
+    cfg = _cases()["rbc64_rk3_dealias"]
+    ns, o = make(cfg), make_oracle(cfg)
+    for _ in range(3):
+        ns.update()
+        ns.update_time()
+        o.update()
+    fname = str(tmp_path / "chk.h5")
+    with __import__("contextlib").redirect_stdout(__import__("io").StringIO()):
+        ns.write(filename=fname)
+        other = rbc2d.NavierStokes(**cfg)
+        other.read(filename=fname)
+    for a, b in zip(ns.field.fields, other.field.fields):
+        assert torch.equal(a.vhat, b.vhat) and torch.equal(a.v, b.v)
+    assert other.time == pytest.approx(ns.time)
+    other.update()
+    ns.update()
+    assert torch.equal(other.T.vhat, ns.T.vhat)
+    # a checkpoint of another resolution is an error, not a silent rebind
+    cfg96 = dict(cfg, shape=(96, 96))
+    big = rbc2d.NavierStokes(**cfg96)
+    with pytest.raises(ValueError):
+        big.read(filename=fname)
+    with pytest.raises(FileNotFoundError):
+        big.read(filename=str(tmp_path / "missing.h5"))
+    # interpolate up and down again: the coefficients of the coarse field survive exactly
+    before = {n: f.vhat.clone() for n, f in zip(ns.field.names, ns.field.fields)}
+    big.interpolate(ns)
+    for f_old, f_new in zip(ns.field.fields, big.field.fields):
+        m0, m1 = f_old.vhat.shape
+        assert torch.equal(f_new.vhat[:m0, :m1], f_old.vhat)
+        assert float(f_new.vhat[m0:, :].abs().max()) == 0.0 and float(f_new.vhat[:, m1:].abs().max()) == 0.0
+        # physical values = the oracle's backward transform of the padded coefficients
+    oT = np.zeros(tuple(big.T.vhat.shape))
+    oT[:o.That_.shape[0], :o.That_.shape[1]] = H(ns.T.vhat)
+    from oracle import pypde_port as P
+    sp = P.Space([P.Basis(96, "CN", 3 / 2), P.Basis(96, "CD", 3 / 2)])
+    assert rel_l2(H(big.T.v), sp.backward(oT)) < 1e-13
+    small = rbc2d.NavierStokes(**cfg)
+    small.interpolate(big)
+    for n, f in zip(small.field.names, small.field.fields):
+        assert torch.equal(f.vhat, before[n])
