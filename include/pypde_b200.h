@@ -124,6 +124,10 @@ int pde_poisson_plan_create(pde_poisson_plan_t *plan, const double *Adiag, const
                             const double *lam, int n, int m, int singular);
 int pde_poisson_plan_destroy(pde_poisson_plan_t plan);
 int pde_poisson_solve(pde_poisson_plan_t plan, double *x, long ldx, void *stream);
+/* Copy one factor table of the plan into a caller-owned DEVICE buffer: which = 0..4 -> l, d, u1, u2, RN(1/d)
+ * ((n x m) doubles, row r = entry of original row r, column = system), 5 -> the m ints that flag the
+ * columns of the singular branch (row/column 0 dropped).  Used to lay the tables out for pde_pass_run. */
+int pde_poisson_plan_export(pde_poisson_plan_t plan, int which, void *dst);
 
 /* ---- dense fp64 contraction -----------------------------------------------------
  * C(m x n) = A(m x k) * B, B given as (k x n) [transB = 0] or (n x k) [transB = 1];
@@ -241,6 +245,92 @@ int pde_dct1_multi(pde_dct_plan_t plan, int mode, int njobs, const double *const
  * col_off is a HOST array of nranks+1 offsets (nranks <= 16). */
 int pde_slab_repack(int dir, double *bundle, double *blocked, int rows, int K, int cols, int nranks,
                     const int *col_off, void *stream);
+
+
+/* ---- fused axis passes ---------------------------------------------------------------
+ * One launch applies a chain of 1-D operators (a small program) to every sequence of several
+ * 2-D arrays: the axis passes of SURVEY.md §8(d).  Replaces, fused, the per-operator calls the
+ * reference makes inside one stage of NavierStokes.update (navier/rbc2d.py:396-434):
+ * to_chebyshev / from_chebyshev (bases/chebyshev.py:287-337 -> tdma.f90:55-106), the derivative
+ * recurrence (differentiate_cheby.f90:28-53), PlanRHS banded products (solver/plans.py:54-74),
+ * Plan_fdma solves (fdma.f90:1-98), Plan_Poisson column solves (fdma.f90:146-195) and the NumPy
+ * axpy's between them (rbc2d.py:252-394).
+ *
+ * layout = axis the operators act along: PDE_PASS_COL (0): sequence q = column q, element i at
+ * p + (i - start) * ld + q; PDE_PASS_ROW (1): sequence q = row q, element i at p + q * ld + (i - start).
+ * An operand may be split along the sequence into nseg segments (segment s holds elements
+ * start[s] .. start[s+1]-1 behind its own base pointer p[s] / leading dimension ld[s]): with peer
+ * mappings of the other ranks' slabs as bases, the loads and stores of the row passes ARE the
+ * distributed transposes of the slab decomposition.  ROW operands need even starts / leading
+ * dimensions and 16-byte aligned bases.
+ *
+ * A sequence lives in shared memory as 16-byte units (x[2m], x[2m+1]); a launch works on
+ * NUP = 32 << lg_segu units (sequences up to 2 NUP elements, zero padded).  Instructions:
+ *   LOAD    buffer <- operand[0..n), zero beyond
+ *   STORE   operand[0..n) <- buffer           (flag ONLY_SEQ: only the sequence with global index off[0])
+ *   AXPY    buffer <- buffer + f0 operand[0..n)   (flag SCALED: f1 buffer + f0 operand;
+ *           flag STENCIL: operand_i + st_i operand_{i-2} with the element table st = p[7])
+ *   SCALE   buffer <- f0 buffer
+ *   SETZ0   element 0 of the sequence with global index off[0] <- 0
+ *   POINT   y[m] = sum_{t<n} C_t[m] x[m + off[t]] on units, C_t = p[t] (double2 per unit, NUP entries)
+ *           or 1 when p[t] is NULL; offsets in [-1, 2], all >= 0 or all <= 0
+ *   DIFF    Chebyshev derivative recurrence, result times f0
+ *   REC1    y[m] = T0[m] b[m] - T1[m] y[m-1]  (flag DESC: y[m+1]); T0 = p[0] (NULL = 1), T1 = p[1]
+ *   REC2    x[m] = T0[m] b[m] - T1[m] x[m+1] - T2[m] x[m+2]; tables p[0..2]
+ * REC tables are in segment order: the entry of unit lane*SEGU + j at [j*32 + lane] (SEGU = 1 << lg_segu);
+ * flag PERSEQ: the tables of sequence q start ld[t] doubles after those of sequence q-1.
+ * Programs and job descriptors are DEVICE arrays (built once by the host-side stepper). */
+#define PDE_PASS_COL 0
+#define PDE_PASS_ROW 1
+#define PDE_PASS_MAX_SEG 8
+#define PDE_PASS_LOAD 1
+#define PDE_PASS_STORE 2
+#define PDE_PASS_AXPY 3
+#define PDE_PASS_SCALE 4
+#define PDE_PASS_SETZ0 5
+#define PDE_PASS_POINT 6
+#define PDE_PASS_DIFF 7
+#define PDE_PASS_REC1 8
+#define PDE_PASS_REC2 9
+#define PDE_PASS_F_DESC 1
+#define PDE_PASS_F_PERSEQ 2
+#define PDE_PASS_F_SCALED 4
+#define PDE_PASS_F_STENCIL 8
+#define PDE_PASS_F_ONLY_SEQ 16
+typedef struct {
+    int op;
+    int n;
+    int flags;
+    int nseg;
+    double f0, f1;
+    const void *p[PDE_PASS_MAX_SEG];
+    long ld[PDE_PASS_MAX_SEG];
+    int start[PDE_PASS_MAX_SEG + 1];
+    int off[4];
+    int pad_;
+} pde_pass_ins;
+typedef struct {
+    const pde_pass_ins *prog;   /* DEVICE pointer */
+    int nins;
+    int nseq;                   /* sequences of this job */
+    int seq0;                   /* global index of sequence 0 (slab decomposition) */
+    int pad_;
+} pde_pass_job;
+int pde_pass_run(int layout, int lg_segu, int njobs, int max_nseq, const pde_pass_job *dev_jobs, void *stream);
+/* sequences per thread block (the strip width of the COL layout) */
+int pde_pass_width(void);
+
+/* ---- peer memory of the slab decomposition (one process per GPU, one node) ---------------
+ * Exchange buffers are cudaMalloc'ed by the library so that their IPC handles (64 bytes) can be
+ * handed to the other ranks (through torch.distributed); pde_ipc_open maps a peer's buffer.
+ * pde_peer_barrier is the device-side rendezvous between the ranks that separates the passes:
+ * dev_peer_flags[s] = mapping of rank s's flag array (nranks 64-bit slots), dev_epoch = this
+ * rank's epoch counter, dev_err is set when a peer did not arrive within ~4 s. */
+int pde_ipc_alloc(void **ptr, long bytes, void *handle64);
+int pde_ipc_open(const void *handle64, void **ptr);
+int pde_ipc_close(void *ptr);
+int pde_ipc_free(void *ptr);
+int pde_peer_barrier(void *const *dev_peer_flags, void *dev_epoch, int rank, int nranks, int *dev_err, void *stream);
 
 /* ---- layout helper ------------------------------------------------------------- */
 /* out(n1 x n0) = in(n0 x n1)^T */

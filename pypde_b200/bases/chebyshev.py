@@ -181,8 +181,9 @@ class GalerkinChebyshev(MetaBase):
         d = np.array([float(Fraction(1) + Fraction(v) * Fraction(v)) for v in s])
         return s[: self.M - 2].copy(), d, s[: self.M - 2].copy()
 
-    def _tables(self):
-        if self._dev is None:
+    def _tables_host(self):
+        """(s, a, den, w): stencil, sub-diagonal of S^T S, Thomas denominators and ratios (tdma.f90:82-89)."""
+        if getattr(self, "_host", None) is None:
             l2, d, u2 = self._init_stencil_inv()
             n = self.M
             w = np.zeros(max(n - 2, 1))
@@ -193,7 +194,12 @@ class GalerkinChebyshev(MetaBase):
                     w[i] = u2[i] / den[i]
             s = self.stencil_diag().copy()
             s[np.abs(s) < 1e-12] = 0
-            self._dev = tuple(C.upload(t) for t in (s, l2, den, w))
+            self._host = (s, l2, den, w)
+        return self._host
+
+    def _tables(self):
+        if self._dev is None:
+            self._dev = tuple(C.upload(t) for t in self._tables_host())
         return self._dev
 
     # -- transforms --------------------------------------------------------------------

@@ -47,17 +47,23 @@ def build(force=False, verbose=False):
     nvcc = _nvcc()
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(ROOT, "include", "pypde_b200.h"))
-    objs, rebuilt = [], False
+    objs, cmds = [], []
     for src in sources():
         s = os.path.join(CSRC, src)
         o = os.path.join(OUT, src[:-3] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            cmd = [nvcc] + ARCH + COMMON + PER_FILE.get(src, []) + ["-c", s, "-o", o]
+            cmds.append([nvcc] + ARCH + COMMON + PER_FILE.get(src, []) + ["-c", s, "-o", o])
+    rebuilt = bool(cmds)
+    if cmds:
+        from concurrent.futures import ThreadPoolExecutor
+
+        def run(cmd):
             if verbose:
                 print(" ".join(cmd))
             subprocess.check_call(cmd)
-            rebuilt = True
+        with ThreadPoolExecutor(max_workers=min(len(cmds), os.cpu_count() or 4)) as ex:
+            list(ex.map(run, cmds))
     if rebuilt or force or _stale(LIB, objs):
         cmd = [nvcc] + ARCH + ["-shared", "-o", LIB] + objs
         if verbose:

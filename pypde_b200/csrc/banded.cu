@@ -330,6 +330,15 @@ int pde_poisson_plan_destroy(pde_poisson_plan_t p)
     return PDE_OK;
 }
 
+int pde_poisson_plan_export(pde_poisson_plan_t p, int which, void *dst)
+{
+    PDE_REQUIRE(p && dst && which >= 0 && which <= 5, "arguments");
+    const double *src[5] = {p->t.l, p->t.d, p->t.u1, p->t.u2, p->t.rd};
+    if (which < 5) PDE_CUDA(cudaMemcpy(dst, src[which], sizeof(double) * (size_t)p->n * p->m, cudaMemcpyDeviceToDevice));
+    else PDE_CUDA(cudaMemcpy(dst, p->t.off, sizeof(int) * (size_t)p->m, cudaMemcpyDeviceToDevice));
+    return PDE_OK;
+}
+
 int pde_poisson_solve(pde_poisson_plan_t p, double *x, long ldx, void *stream)
 {
     PDE_REQUIRE(p && x, "null pointer");

@@ -39,8 +39,10 @@ class NavierStokes(NavierStokesBase, NavierStokesSteadyState, Integrator):
         """dealias_grid: "fft" (default) evaluates the 3/2-rule products on the next
         FFT-friendly Gauss-Lobatto grid >= 3N/2 (same truncated coefficients up to rounding);
         "reference" uses exactly int(3N/2) points like the reference.
-        stepper: "fast" (default) runs the batched stage of fast_stepper.FastStepper,
-        "reference" the operator-by-operator sequence of the reference (update_reference).
+        stepper: "fast" (default) runs the stage as fused axis passes (pass_stepper.PassStepper; grids with
+        odd sizes fall back to "batched"), "batched" one batched launch per operator
+        (fast_stepper.FastStepper), "reference" the operator-by-operator sequence of the reference
+        (update_reference).
         graph: capture the whole time step in a CUDA graph (removes launch overhead on
         small grids).
         slab: distribute the step over the ranks of the default torch.distributed process group
@@ -218,7 +220,7 @@ class NavierStokes(NavierStokesBase, NavierStokesSteadyState, Integrator):
 
     def update(self):
         """One time step = nstage IMEX stages (rbc2d.py:396-434)."""
-        if self._stepper_kind != "fast" or self.beta != 1.0:
+        if self._stepper_kind not in ("fast", "batched") or self.beta != 1.0:
             return self.update_reference()
         if self._fast is None:
             if self._slab:
@@ -226,7 +228,11 @@ class NavierStokes(NavierStokesBase, NavierStokesSteadyState, Integrator):
                 self._fast = SlabStepper(self)
             else:
                 from .fast_stepper import FastStepper
-                self._fast = FastStepper(self)
+                from .pass_stepper import PassStepper
+                if self._stepper_kind == "fast" and PassStepper.supported(self):
+                    self._fast = PassStepper(self)       # fused axis passes (even grids up to 4096)
+                else:
+                    self._fast = FastStepper(self)       # one launch per operator ("batched", or odd sizes)
         if not self._use_graph:
             for rk in range(self.nstage):
                 self._fast.stage(rk)

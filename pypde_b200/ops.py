@@ -126,6 +126,7 @@ class Band:
         d = np.ascontiguousarray(diags, dtype=np.float64)
         self.ndiag, self.n_out = d.shape
         self.n_in = int(n_in)
+        self.host = d                      # host copy (table layouts of the fused passes)
         self.diags = C.upload(d)
         self._off = (ctypes.c_int * self.ndiag)(*self.offsets)
 
