@@ -203,12 +203,17 @@ class OpTimer:
         fs = ns._fast
         st = _cabi.stream()
         for rk in range(ns.nstage):
+            npass = 0
             for fn, args in fs.stage_calls[rk].calls:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 _cabi.check(fn(*args, st))
                 e1.record()
-                self.records.append((getattr(fn, "__name__", "call"), args, e0, e1))
+                name = getattr(fn, "__name__", "call")
+                if name == "pde_pass_run":
+                    npass += 1
+                    name = "pde_pass_run[P%s%d]" % ("Y" if args[0] else "X", npass)
+                self.records.append((name, args, e0, e1))
         torch.cuda.synchronize()
 
     def summary(self):

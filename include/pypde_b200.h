@@ -266,23 +266,30 @@ int pde_slab_repack(int dir, double *bundle, double *blocked, int rows, int K, i
  *
  * A sequence lives in shared memory as 16-byte units (x[2m], x[2m+1]); a launch works on
  * NUP = 32 << lg_segu units (sequences up to 2 NUP elements, zero padded).  Instructions:
+ *   TABLES  stage n <= 4 recurrence tables p[k] (segment order, NUP double2 each) in the shared-memory slots
+ *           k = 0..n-1; executed once per thread block and job
  *   LOAD    buffer <- operand[0..n), zero beyond
  *   STORE   operand[0..n) <- buffer           (flag ONLY_SEQ: only the sequence with global index off[0])
  *   AXPY    buffer <- buffer + f0 operand[0..n)   (flag SCALED: f1 buffer + f0 operand;
  *           flag STENCIL: operand_i + st_i operand_{i-2} with the element table st = p[7])
+ *   LINCOMB buffer <- [buffer +] sum_k coef[k] G_k for nseg <= PDE_PASS_MAX_TERMS unsegmented operands
+ *           p[k] / ld[k] with start[k] valid elements each (flag ACCUM keeps the buffer)
  *   SCALE   buffer <- f0 buffer
  *   SETZ0   element 0 of the sequence with global index off[0] <- 0
  *   POINT   y[m] = sum_{t<n} C_t[m] x[m + off[t]] on units, C_t = p[t] (double2 per unit, NUP entries)
  *           or 1 when p[t] is NULL; offsets in [-1, 2], all >= 0 or all <= 0
  *   DIFF    Chebyshev derivative recurrence, result times f0
- *   REC1    y[m] = T0[m] b[m] - T1[m] y[m-1]  (flag DESC: y[m+1]); T0 = p[0] (NULL = 1), T1 = p[1]
- *   REC2    x[m] = T0[m] b[m] - T1[m] x[m+1] - T2[m] x[m+2]; tables p[0..2]
- * REC tables are in segment order: the entry of unit lane*SEGU + j at [j*32 + lane] (SEGU = 1 << lg_segu);
- * flag PERSEQ: the tables of sequence q start ld[t] doubles after those of sequence q-1.
- * Programs and job descriptors are DEVICE arrays (built once by the host-side stepper). */
+ *   REC1    y[m] = T0[m] b[m] - T1[m] y[m-1]  (flag DESC: y[m+1]); T0 optional (= 1)
+ *   REC2    x[m] = T0[m] b[m] - T1[m] x[m+1] - T2[m] x[m+2]
+ * REC tables: table k is the shared-memory slot slot[k] (>= 0, staged by TABLES) or, with slot[k] < 0, the
+ * global pointer p[k] (NULL = absent); segment order: the entry of unit lane*SEGU + j at [j*32 + lane]
+ * (SEGU = 1 << lg_segu); flag PERSEQ (global tables): the tables of sequence q start ld[k] doubles after
+ * those of sequence q-1.
+ * Programs (<= 16 instructions) and job descriptors are DEVICE arrays (built once by the host-side stepper). */
 #define PDE_PASS_COL 0
 #define PDE_PASS_ROW 1
 #define PDE_PASS_MAX_SEG 8
+#define PDE_PASS_MAX_TERMS 6
 #define PDE_PASS_LOAD 1
 #define PDE_PASS_STORE 2
 #define PDE_PASS_AXPY 3
@@ -292,22 +299,26 @@ int pde_slab_repack(int dir, double *bundle, double *blocked, int rows, int K, i
 #define PDE_PASS_DIFF 7
 #define PDE_PASS_REC1 8
 #define PDE_PASS_REC2 9
+#define PDE_PASS_TABLES 10
+#define PDE_PASS_LINCOMB 11
 #define PDE_PASS_F_DESC 1
 #define PDE_PASS_F_PERSEQ 2
 #define PDE_PASS_F_SCALED 4
 #define PDE_PASS_F_STENCIL 8
 #define PDE_PASS_F_ONLY_SEQ 16
+#define PDE_PASS_F_ACCUM 32
 typedef struct {
     int op;
     int n;
     int flags;
     int nseg;
     double f0, f1;
+    double coef[PDE_PASS_MAX_TERMS];
     const void *p[PDE_PASS_MAX_SEG];
     long ld[PDE_PASS_MAX_SEG];
     int start[PDE_PASS_MAX_SEG + 1];
     int off[4];
-    int pad_;
+    int slot[3];
 } pde_pass_ins;
 typedef struct {
     const pde_pass_ins *prog;   /* DEVICE pointer */
@@ -317,8 +328,8 @@ typedef struct {
     int pad_;
 } pde_pass_job;
 int pde_pass_run(int layout, int lg_segu, int njobs, int max_nseq, const pde_pass_job *dev_jobs, void *stream);
-/* sequences per thread block (the strip width of the COL layout) */
-int pde_pass_width(void);
+/* sequences per thread block (the strip width of the COL layout) for a given lg_segu */
+int pde_pass_width(int lg_segu);
 
 /* ---- peer memory of the slab decomposition (one process per GPU, one node) ---------------
  * Exchange buffers are cudaMalloc'ed by the library so that their IPC handles (64 bytes) can be

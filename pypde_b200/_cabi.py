@@ -52,7 +52,7 @@ SIGNATURES = {
     "pde_poisson_solve": (_c_int, [ctypes.c_void_p, _c_dp, _c_long, ctypes.c_void_p]),
     "pde_poisson_plan_export": (_c_int, [ctypes.c_void_p, _c_int, ctypes.c_void_p]),
     "pde_pass_run": (_c_int, [_c_int, _c_int, _c_int, _c_int, ctypes.c_void_p, ctypes.c_void_p]),
-    "pde_pass_width": (_c_int, []),
+    "pde_pass_width": (_c_int, [_c_int]),
     "pde_ipc_alloc": (_c_int, [ctypes.POINTER(ctypes.c_void_p), _c_long, ctypes.c_void_p]),
     "pde_ipc_open": (_c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p)]),
     "pde_ipc_close": (_c_int, [ctypes.c_void_p]),

@@ -130,12 +130,12 @@ class PassStepper(FastStepper):
         self._dct(calls, self.plan0, ops.FWD, 0, [f[:, : N1] for f in self.F3], [cv[: N0] for cv in self.conv])
         # ---- PX3: z = Ax^-1 Bx (Sy Sx F + rhs)
         L = PS.PassLaunch(PS.COL, N0, self.tables)
-        p = L.job(N1).load(eF["U"]).axpy(-dt * a, self.dpdx).axpy(-dt, conv["U"])
+        p = L.job(N1).lincomb([(1.0, eF["U"]), (-dt * a, self.dpdx), (-dt, conv["U"])])
         p.band(solver["U"].plan_for_rhs[0].band).fdma(solver["U"].plan_for_lhs[0]).store(zF["U"])
-        p = L.job(N1).load(eF["V"]).axpy(-dt * a, self.dpdz).axpy(-dt, conv["V"]).axpy(dt * a, eF["T"])
-        p.axpy(dt * a, self.tbc_cheby)
+        p = L.job(N1).lincomb([(1.0, eF["V"]), (-dt * a, self.dpdz), (-dt, conv["V"]), (dt * a, eF["T"]),
+                               (dt * a, self.tbc_cheby)])
         p.band(solver["V"].plan_for_rhs[0].band).fdma(solver["V"].plan_for_lhs[0]).store(zF["V"])
-        p = L.job(N1).load(eF["T"]).axpy(-dt, conv["T"]).axpy(dt * a * ns.kappa, self.dTbcdz2)
+        p = L.job(N1).lincomb([(1.0, eF["T"]), (-dt, conv["T"]), (dt * a * ns.kappa, self.dTbcdz2)])
         p.band(solver["T"].plan_for_rhs[0].band).fdma(solver["T"].plan_for_lhs[0]).store(zF["T"])
         add(L)
         # ---- PY4: F* = Ay^-1 By z; y parts of the divergence
@@ -170,10 +170,10 @@ class PassStepper(FastStepper):
         add(L)
         # ---- PX8: velocity projection and pressure update
         L = PS.PassLaunch(PS.COL, N0, self.tables)
-        L.job(M1).load(self.bU[:M0]).stencil(xbP).diff(sx).from_cheb(xb["U"]).scale(-1.0).axpy(1.0, U).store(U)
-        L.job(M1).load(self.bV[:M0]).stencil(xbP).from_cheb(xb["V"]).scale(-1.0).axpy(1.0, V).store(V)
-        L.job(N1).load(self.e1[:M0]).stencil(xbP).scale(1.0 / (dt * a)).axpy(1.0, pres).axpy(-(1.0 * ns.nu), self.div) \
-            .store(pres)
+        L.job(M1).load(self.bU[:M0]).stencil(xbP).diff(sx).from_cheb(xb["U"]).axpy(1.0, U, scale_buf=-1.0).store(U)
+        L.job(M1).load(self.bV[:M0]).stencil(xbP).from_cheb(xb["V"]).axpy(1.0, V, scale_buf=-1.0).store(V)
+        L.job(N1).load(self.e1[:M0]).stencil(xbP).scale(1.0 / (dt * a)) \
+            .lincomb([(1.0, pres), (-(1.0 * ns.nu), self.div)], accumulate=True).store(pres)
         add(L)
         calls.keep += [T, U, V, P, pres]
         return calls

@@ -224,8 +224,13 @@ class NavierStokes(NavierStokesBase, NavierStokesSteadyState, Integrator):
             return self.update_reference()
         if self._fast is None:
             if self._slab:
-                from .slab_stepper import SlabStepper
-                self._fast = SlabStepper(self)
+                import torch.distributed as dist
+                from .pass_slab_stepper import PassSlabStepper
+                if self._stepper_kind == "fast" and PassSlabStepper.supported(self, dist.get_world_size()):
+                    self._fast = PassSlabStepper(self)   # peer-memory row passes, no NCCL on the data path
+                else:
+                    from .slab_stepper import SlabStepper
+                    self._fast = SlabStepper(self)       # NCCL all-to-all transposes ("batched")
             else:
                 from .fast_stepper import FastStepper
                 from .pass_stepper import PassStepper
@@ -255,6 +260,16 @@ class NavierStokes(NavierStokesBase, NavierStokesSteadyState, Integrator):
         """Slab mode: gather the distributed state into T, U, V, pres of every rank."""
         if self._slab and self._fast is not None:
             self._fast.gather()
+
+    def close(self):
+        """Slab mode: release the CUDA graph and the peer mappings (call on every rank before
+        torch.distributed.destroy_process_group)."""
+        import torch
+        torch.cuda.synchronize()
+        self._graph = None
+        fs, self._fast = self._fast, None
+        if fs is not None and hasattr(fs, "close"):
+            fs.close()
 
     def _update_graph(self):
         fs = self._fast

@@ -23,17 +23,20 @@ import torch
 from . import _cabi as C
 
 MAX_SEG = 8
+MAX_TERMS = 6
+MAX_INS = 16
+SLOTS = 4
 COL, ROW = 0, 1
-LOAD, STORE, AXPY, SCALE, SETZ0, POINT, DIFF, REC1, REC2 = 1, 2, 3, 4, 5, 6, 7, 8, 9
-F_DESC, F_PERSEQ, F_SCALED, F_STENCIL, F_ONLY_SEQ = 1, 2, 4, 8, 16
+LOAD, STORE, AXPY, SCALE, SETZ0, POINT, DIFF, REC1, REC2, TABLES, LINCOMB = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
+F_DESC, F_PERSEQ, F_SCALED, F_STENCIL, F_ONLY_SEQ, F_ACCUM = 1, 2, 4, 8, 16, 32
 
 
 class PassIns(ctypes.Structure):
     """pde_pass_ins (include/pypde_b200.h)"""
     _fields_ = [("op", ctypes.c_int), ("n", ctypes.c_int), ("flags", ctypes.c_int), ("nseg", ctypes.c_int),
-                ("f0", ctypes.c_double), ("f1", ctypes.c_double), ("p", ctypes.c_void_p * MAX_SEG),
-                ("ld", ctypes.c_long * MAX_SEG), ("start", ctypes.c_int * (MAX_SEG + 1)), ("off", ctypes.c_int * 4),
-                ("pad_", ctypes.c_int)]
+                ("f0", ctypes.c_double), ("f1", ctypes.c_double), ("coef", ctypes.c_double * MAX_TERMS),
+                ("p", ctypes.c_void_p * MAX_SEG), ("ld", ctypes.c_long * MAX_SEG),
+                ("start", ctypes.c_int * (MAX_SEG + 1)), ("off", ctypes.c_int * 4), ("slot", ctypes.c_int * 3)]
 
 
 class PassJob(ctypes.Structure):
@@ -181,12 +184,41 @@ class Program:
 
     def __init__(self, launch, nseq, seq0=0):
         self.L, self.nseq, self.seq0, self.ins = launch, int(nseq), int(seq0), []
+        self.slots = []             # shared-memory table slots of this job: list of device tables
 
     def _new(self, op):
         i = PassIns()
         i.op, i.nseg = op, 1
+        for k in range(3):
+            i.slot[k] = -1
         self.ins.append(i)
         return i
+
+    def _slot(self, tab):
+        """shared-memory slot of a (job-wide) recurrence table, or -1 when the four slots are taken"""
+        for k, t in enumerate(self.slots):
+            if t is tab:
+                return k
+        if len(self.slots) < SLOTS:
+            self.slots.append(tab)
+            return len(self.slots) - 1
+        return -1
+
+    def finish(self):
+        """instruction list with the TABLES prologue"""
+        out = []
+        if self.slots:
+            i = PassIns()
+            i.op, i.n, i.nseg = TABLES, len(self.slots), 1
+            for k, t in enumerate(self.slots):      # positional: table k -> slot k
+                i.p[k] = t.data_ptr()
+            for k in range(3):
+                i.slot[k] = -1
+            out.append(i)
+        out += self.ins
+        if len(out) > MAX_INS:
+            raise ValueError("axis-pass program too long (%d > %d instructions)" % (len(out), MAX_INS))
+        return out
 
     def _opnd(self, x):
         if isinstance(x, Operand):
@@ -256,25 +288,42 @@ class Program:
         self._new(DIFF).f0 = 1.0 / float(div)
         return self
 
-    def rec1(self, t0, t1, desc=False, perseq=None):
-        i = self._new(REC1)
-        i.flags = (F_DESC if desc else 0) | (F_PERSEQ if perseq else 0)
-        i.p[0] = t0.data_ptr() if t0 is not None else None
-        i.p[1] = t1.data_ptr()
-        if perseq:
-            i.ld[0] = i.ld[1] = int(perseq)
-        self.L.keep += [t0, t1]
+    def lincomb(self, terms, accumulate=False):
+        """buffer = [buffer +] sum coef * x over (coef, tensor) terms (local, unsegmented operands)"""
+        assert 1 <= len(terms) <= MAX_TERMS
+        i = self._new(LINCOMB)
+        i.nseg = len(terms)
+        i.flags = F_ACCUM if accumulate else 0
+        for k, (coef, x) in enumerate(terms):
+            o = self._opnd(x)
+            assert len(o.ptrs) == 1
+            i.p[k], i.ld[k], i.start[k], i.coef[k] = o.ptrs[0], o.lds[0], o.n, float(coef)
         return self
 
-    def rec2(self, t0, t1, t2, perseq=None):
-        i = self._new(REC2)
-        i.flags = F_DESC | (F_PERSEQ if perseq else 0)
-        for k, t in enumerate((t0, t1, t2)):
-            i.p[k] = t.data_ptr()
+    def _rec(self, op, tabs, desc, perseq):
+        i = self._new(op)
+        i.flags = (F_DESC if desc else 0) | (F_PERSEQ if perseq else 0)
+        # a recurrence runs either entirely from shared slots or entirely from global tables
+        slots = [-1] * len(tabs)
+        if not perseq:
+            before = list(self.slots)
+            slots = [self._slot(t) if t is not None else -1 for t in tabs]
+            if any(s < 0 and t is not None for s, t in zip(slots, tabs)):
+                self.slots = before
+                slots = [-1] * len(tabs)
+        for k, t in enumerate(tabs):
+            i.slot[k] = slots[k]
+            i.p[k] = t.data_ptr() if t is not None else None
             if perseq:
                 i.ld[k] = int(perseq)
-        self.L.keep += [t0, t1, t2]
+        self.L.keep += list(tabs)
         return self
+
+    def rec1(self, t0, t1, desc=False, perseq=None):
+        return self._rec(REC1, (t0, t1), desc, perseq)
+
+    def rec2(self, t0, t1, t2, perseq=None):
+        return self._rec(REC2, (t0, t1, t2), True, perseq)
 
     # -- composites on the framework's objects
     def stencil(self, base):
@@ -351,7 +400,8 @@ class PassLaunch:
 
     def finalize(self):
         nj = len(self.jobs)
-        nins = sum(len(j.ins) for j in self.jobs)
+        progs = [j.finish() for j in self.jobs]
+        nins = sum(len(pr) for pr in progs)
         isz, jsz = ctypes.sizeof(PassIns), ctypes.sizeof(PassJob)
         buf = torch.empty(((jsz * nj + 15) // 16 * 16 + isz * nins,), dtype=torch.uint8, device=C.device())
         base = buf.data_ptr()
@@ -359,9 +409,9 @@ class PassLaunch:
         jobs = (PassJob * nj)()
         ins = (PassIns * max(nins, 1))()
         k = 0
-        for j, pr in enumerate(self.jobs):
-            jobs[j].prog, jobs[j].nins, jobs[j].nseq, jobs[j].seq0 = base + ioff + isz * k, len(pr.ins), pr.nseq, pr.seq0
-            for i in pr.ins:
+        for j, (pr, ins_list) in enumerate(zip(self.jobs, progs)):
+            jobs[j].prog, jobs[j].nins, jobs[j].nseq, jobs[j].seq0 = base + ioff + isz * k, len(ins_list), pr.nseq, pr.seq0
+            for i in ins_list:
                 ctypes.memmove(ctypes.byref(ins[k]), ctypes.byref(i), isz)
                 k += 1
         host = bytes(jobs) + b"\0" * (ioff - jsz * nj) + bytes(ins)[: isz * nins]

@@ -214,3 +214,29 @@ def test_many_jobs_one_launch():
         if j % 2:
             want = np.ascontiguousarray(K.diff_2d(np.ascontiguousarray(want.T)).T) / 0.5
         assert rel_l2(outs[j].cpu().numpy(), want * j) < TOL
+
+
+@pytest.mark.parametrize("axis", [0, 1])
+@pytest.mark.parametrize("n,nseq", [(66, 7), (2048, 19)])
+def test_lincomb(axis, n, nseq):
+    """buffer = sum_k coef_k G_k with operands of different valid lengths, then accumulated onto the buffer."""
+    torch, C, PS = _mods()
+    rng = np.random.default_rng(n + axis)
+    hs = [_arr(rng, n - 2 * (k % 2), nseq, axis) for k in range(5)]
+    ds = [_dev(torch, h) for h in hs]
+    coef = [1.0, -0.25, 3.0, 1e-3, -7.5]
+    shape = (n, nseq) if axis == 0 else (nseq, n)
+    out1 = torch.zeros(shape, dtype=torch.float64, device="cuda")
+    out2 = torch.zeros(shape, dtype=torch.float64, device="cuda")
+    _run(PS, axis, n, lambda p: p.lincomb(list(zip(coef, ds))).store(out1)
+         .lincomb([(2.0, ds[0]), (-1.0, ds[2])], accumulate=True).store(out2), nseq)
+    want = np.zeros(shape)
+    for cf, h in zip(coef, hs):
+        if axis == 0:
+            want[: h.shape[0]] += cf * h
+        else:
+            want[:, : h.shape[1]] += cf * h
+    assert rel_l2(out1.cpu().numpy(), want) < 1e-15
+    want2 = want.copy()
+    want2 += 2.0 * hs[0] - hs[2]
+    assert rel_l2(out2.cpu().numpy(), want2) < 1e-15

@@ -60,3 +60,64 @@ def test_bundled_transposes_gloo(world, rows, cols, K):
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, rows, cols, K, out), nprocs=world, join=True)
     assert all(out[r] for r in range(world))
+
+
+# ---------------------------------------------------------------------------------------------------
+# peer-memory slab decomposition (navier/peer.py): layout arithmetic and the segment description of the
+# row passes, emulated with numpy buffers as "peer memory"; rendezvous of the IPC handles over gloo.
+# ---------------------------------------------------------------------------------------------------
+def test_slab_layout_and_row_segments():
+    from pypde_b200.navier.peer import SlabLayout, partition as part4, row_segments
+    assert part4(2048, 8, 4) == [(256 * r, 256) for r in range(8)]
+    assert [w for _, w in part4(66, 4, 4)] == [20, 16, 16, 14] and sum(w for _, w in part4(66, 4, 4)) == 66
+    for N0, N1, D0, P in ((64, 64, 97, 2), (48, 64, 73, 4), (2048, 2048, 3073, 8), (130, 132, 197, 3)):
+        lays = [SlabLayout(N0, N1, D0, D0, P, r) for r in range(P)]
+        assert sum(l.W for l in lays) == N1 and sum(l.N0r for l in lays) == N0 and sum(l.D0r for l in lays) == D0
+        assert sum(l.M1c for l in lays) == N1 - 2 and sum(l.M0r for l in lays) == N0 - 2
+        assert all(l.c0 % 4 == 0 and l.W % 2 == 0 for l in lays)
+        # emulate: every rank owns a (rows x Wmax) slab of a global (N0 x ncols) array inside a flat buffer
+        W = lays[0].Wmax
+        rng = np.random.default_rng(P)
+        for ncols in (N1, N1 - 2):
+            G = rng.standard_normal((N0, ncols))
+            offset = 256
+            bufs = []
+            for l in lays:
+                b = np.zeros(offset // 8 + N0 * W)
+                w = l.ncols_local(ncols)
+                b[offset // 8:].reshape(N0, W)[:, :w] = G[:, l.c0:l.c0 + w]
+                bufs.append(b)
+            bases = [1000000 * (s + 1) for s in range(P)]          # fake addresses, 8-byte "memory" = bufs
+            for l in lays:
+                ptrs, lds, starts = row_segments(bases, offset, W, l.r0, l.col_starts(ncols), ncols)
+                assert starts[-1] == ncols and all(s % 2 == 0 for s in starts[:-1])
+                for q in (0, l.N0r - 1):
+                    row = np.empty(ncols)
+                    for i in range(ncols):
+                        s = max(k for k in range(P) if starts[k] <= i)
+                        addr = ptrs[s] + 8 * (q * lds[s] + i - starts[s])       # the kernel's formula
+                        row[i] = bufs[s][(addr - bases[s]) // 8]
+                    assert np.array_equal(row, G[l.r0 + q])
+    with pytest.raises(ValueError):
+        SlabLayout(16, 16, 25, 25, 8, 0)
+
+
+def _handles_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from pypde_b200.navier.peer import exchange_handles
+        mine = bytes([rank]) * 64
+        got = exchange_handles(mine)
+        out[rank] = got == [bytes([r]) * 64 for r in range(world)]
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ipc_handle_rendezvous_gloo():
+    port = _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_handles_worker, args=(2, port, out), nprocs=2, join=True)
+    assert all(out[r] for r in range(2))
