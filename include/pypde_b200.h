@@ -271,7 +271,8 @@ int pde_slab_repack(int dir, double *bundle, double *blocked, int rows, int K, i
  *   LOAD    buffer <- operand[0..n), zero beyond
  *   STORE   operand[0..n) <- buffer           (flag ONLY_SEQ: only the sequence with global index off[0])
  *   AXPY    buffer <- buffer + f0 operand[0..n)   (flag SCALED: f1 buffer + f0 operand;
- *           flag STENCIL: operand_i + st_i operand_{i-2} with the element table st = p[7])
+ *           flag STENCIL: the image operand_i + st_i operand_{i-2}, i < n + 2, of the n operand entries,
+ *           with the element table st = p[7])
  *   LINCOMB buffer <- [buffer +] sum_k coef[k] G_k for nseg <= PDE_PASS_MAX_TERMS unsegmented operands
  *           p[k] / ld[k] with start[k] valid elements each (flag ACCUM keeps the buffer)
  *   SCALE   buffer <- f0 buffer

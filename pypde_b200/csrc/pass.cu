@@ -250,43 +250,46 @@ __device__ __forceinline__ void op_store(const Ctx &c, const pde_pass_ins &I)
 // operand; flag STENCIL: G_i = g_i + st_i g_{i-2} with the element table st = p[7] (st_i = s_{i-2}, st_0 = st_1 = 0)
 // Loads are issued in independent batches of PB before they are consumed.
 // ------------------------------------------------------------------------------------------------
-template <bool COL, class Ctx>
-__device__ __forceinline__ void op_axpy(const Ctx &c, const pde_pass_ins &I)
+template <bool COL, bool STEN, class Ctx>
+__device__ __forceinline__ void axpy_impl(const Ctx &c, const pde_pass_ins &I)
 {
-    const int n = I.n;
+    // STEN: the operand has n valid entries, its image G_i = g_i + st_i g_{i-2} has n + 2
+    const int n = I.n, nout = STEN ? n + 2 : n;
     const bool scaled = (I.flags & PDE_PASS_F_SCALED) != 0;
     const double f0 = I.f0, f1 = scaled ? I.f1 : 1.0;
-    const bool sten = (I.flags & PDE_PASS_F_STENCIL) != 0;
     const bool one = I.nseg == 1;
     const double *st = reinterpret_cast<const double *>(I.p[PDE_PASS_MAX_SEG - 1]);
     if (!COL) {
         if (!c.live) return;
+        constexpr int AB = STEN ? 4 : 8;
         const double *row0 = reinterpret_cast<const double *>(I.p[0]) + (long)c.q * I.ld[0];
         double2 *bb = c.buf + RowMap<Ctx>::base(c.lane);
 #pragma unroll 1
-        for (int k0 = 0; k0 < Ctx::SEGU; k0 += PB) {
-            double2 g[PB], h[PB], t[PB];
+        for (int k0 = 0; k0 < Ctx::SEGU; k0 += AB) {
+            double2 g[AB], h[AB], t[AB];
 #pragma unroll
-            for (int e = 0; e < PB; ++e) {
+            for (int e = 0; e < AB; ++e) {
                 const int i = 2 * c.lane + 64 * (k0 + e);
                 g[e] = h[e] = t[e] = d2(0.0, 0.0);
-                if (k0 + e < Ctx::SEGU && i < n) {
-                    const double *src = one ? row0 + i : elem_addr<false>(I, seg_of(I, i), c.q, i);
-                    if (i + 1 < n) g[e] = __ldg(reinterpret_cast<const double2 *>(src));
-                    else g[e].x = __ldg(src);
-                    if (sten && i >= 2) {
+                if (k0 + e < Ctx::SEGU && i < nout) {
+                    if (i < n) {
+                        const double *src = one ? row0 + i : elem_addr<false>(I, seg_of(I, i), c.q, i);
+                        if (i + 1 < n) g[e] = __ldg(reinterpret_cast<const double2 *>(src));
+                        else g[e].x = __ldg(src);
+                    }
+                    if (STEN && i >= 2) {
                         const double *s2 = one ? row0 + i - 2 : elem_addr<false>(I, seg_of(I, i - 2), c.q, i - 2);
-                        h[e] = __ldg(reinterpret_cast<const double2 *>(s2));
+                        if (i - 1 < n) h[e] = __ldg(reinterpret_cast<const double2 *>(s2));
+                        else h[e].x = __ldg(s2);
                         t[e] = __ldg(reinterpret_cast<const double2 *>(st + i));
-                        if (i + 1 >= n) t[e].y = 0.0;
                     }
                 }
             }
 #pragma unroll
-            for (int e = 0; e < PB; ++e) {
+            for (int e = 0; e < AB; ++e) {
                 const int k = k0 + e;
-                if (k < Ctx::SEGU && (scaled || 2 * c.lane + 64 * k < n)) {
-                    const double2 gg = fma2(t[e], h[e], g[e]);
+                if (k < Ctx::SEGU && (scaled || 2 * c.lane + 64 * k < nout)) {
+                    const double2 gg = STEN ? fma2(t[e], h[e], g[e]) : g[e];
                     double2 &b = bb[RowMap<Ctx>::off(k)];
                     b = scaled ? d2(fma(f0, gg.x, f1 * b.x), fma(f0, gg.y, f1 * b.y)) : fmas(f0, gg, b);
                 }
@@ -296,35 +299,43 @@ __device__ __forceinline__ void op_axpy(const Ctx &c, const pde_pass_ins &I)
     } else {
         const ColMap<Ctx> cm;
         if (c.q0 + cm.col >= c.nseq) return;
+        constexpr int AB = STEN ? 8 : 16;          // 8-byte loads: many in flight per thread
         double *bb = reinterpret_cast<double *>(c.all + cm.col * Ctx::BUFU) + cm.base();
         const long ld0 = I.ld[0];
         const double *col0 = reinterpret_cast<const double *>(I.p[0]) + c.q0 + cm.col;
 #pragma unroll 1
-        for (int j0 = 0; j0 < ColMap<Ctx>::STEPS; j0 += PB) {
-            double g[PB], h[PB], t[PB];
+        for (int j0 = 0; j0 < ColMap<Ctx>::STEPS; j0 += AB) {
+            double g[AB], h[AB], t[AB];
 #pragma unroll
-            for (int e = 0; e < PB; ++e) {
+            for (int e = 0; e < AB; ++e) {
                 const int r = cm.r0 + 32 * (j0 + e);
                 g[e] = h[e] = t[e] = 0.0;
-                if (j0 + e < ColMap<Ctx>::STEPS && r < n) {
-                    g[e] = __ldg(one ? col0 + (long)r * ld0 : elem_addr<true>(I, seg_of(I, r), c.q0 + cm.col, r));
-                    if (sten && r >= 2) {
+                if (j0 + e < ColMap<Ctx>::STEPS && r < nout) {
+                    if (r < n) g[e] = __ldg(one ? col0 + (long)r * ld0 : elem_addr<true>(I, seg_of(I, r), c.q0 + cm.col, r));
+                    if (STEN && r >= 2) {
                         h[e] = __ldg(one ? col0 + (long)(r - 2) * ld0 : elem_addr<true>(I, seg_of(I, r - 2), c.q0 + cm.col, r - 2));
                         t[e] = __ldg(st + r);
                     }
                 }
             }
 #pragma unroll
-            for (int e = 0; e < PB; ++e) {
+            for (int e = 0; e < AB; ++e) {
                 const int j = j0 + e;
-                if (j < ColMap<Ctx>::STEPS && (scaled || cm.r0 + 32 * j < n)) {
-                    const double gg = fma(t[e], h[e], g[e]);
+                if (j < ColMap<Ctx>::STEPS && (scaled || cm.r0 + 32 * j < nout)) {
+                    const double gg = STEN ? fma(t[e], h[e], g[e]) : g[e];
                     double &b = bb[ColMap<Ctx>::off(j)];
                     b = scaled ? fma(f0, gg, f1 * b) : fma(f0, gg, b);
                 }
             }
         }
     }
+}
+
+template <bool COL, class Ctx>
+__device__ __forceinline__ void op_axpy(const Ctx &c, const pde_pass_ins &I)
+{
+    if (I.flags & PDE_PASS_F_STENCIL) axpy_impl<COL, true, Ctx>(c, I);
+    else axpy_impl<COL, false, Ctx>(c, I);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -335,7 +346,7 @@ __device__ __forceinline__ void op_axpy(const Ctx &c, const pde_pass_ins &I)
 template <bool COL, class Ctx>
 __device__ __forceinline__ void op_lincomb(const Ctx &c, const pde_pass_ins &I)
 {
-    constexpr int LB = 2, KMAX = PDE_PASS_MAX_TERMS;
+    constexpr int LB = COL ? 8 : 4, KMAX = PDE_PASS_MAX_TERMS;
     const int K = I.nseg;
     const bool accum = (I.flags & PDE_PASS_F_ACCUM) != 0;
     if (!COL) {
@@ -785,11 +796,13 @@ __global__ void __launch_bounds__(LG <= 5 ? 256 : 64) k_pass(const pde_pass_job 
     // flattened (job, strip) list, split into contiguous chunks over the CTAs
     long total = 0;
     for (int j = 0; j < njobs; ++j) total += (jobref(j).nseq + W - 1) / W;
-    const long lo = total * blockIdx.x / gridDim.x, hi = total * (blockIdx.x + 1) / gridDim.x;
+    // strips are dealt round-robin: at any moment the CTAs of the grid work on ADJACENT strips (COL: neighbouring
+    // 64-byte pieces of the same rows -> whole DRAM pages; with contiguous chunks per CTA every page was shared by
+    // ~4 CTAs only)
     int job = 0;
     long jstart = 0;
     int cur = -1, nins = 0, jstrips = (jobref(0).nseq + W - 1) / W;
-    for (long idx = lo; idx < hi; ++idx) {
+    for (long idx = blockIdx.x; idx < total; idx += gridDim.x) {
         while (idx >= jstart + jstrips) {
             jstart += jstrips;
             ++job;

@@ -7,9 +7,10 @@ sequence once, apply a chain of operators in shared memory (pde_pass_run, csrc/p
 ("axis-pass model").  X = along axis 0 (per column), Y = along axis 1 (per row):
 
     PX1  F -> Sx F, dx Sx F / sx                         (F = U, V, T;  pres -> dpdx)
-    PY2  -> eF = Sy Sx F, gF = dz eF / sz, fF = Sy dx Sx F / sx;  pres -> dpdz
+    PY2  -> eF = Sy Sx F, gF = dz eF / sz, fF = Sy dx Sx F / sx;
+         rest_F = eF + (pressure gradient, buoyancy, boundary terms)
          8 backward 2-D DCTs, products, 3 forward 2-D DCTs    (dct_fft*.cu, batched.cu; unchanged)
-    PX3  zF = Ax^-1 Bx (eF + rhs_F)                       (rhs_F: pressure gradient, convection, buoyancy, BC)
+    PX3  zF = Ax^-1 Bx (rest_F - dt conv_F)
     PY4  F* = Ay^-1 By zF;  y parts of div(U*, V*)
     PX5  div, q = Bx div
          R = q Hy^T                                          (gemm.cu)
@@ -58,7 +59,8 @@ class PassStepper(FastStepper):
         self.e3 = [n(N0, N1) for _ in range(3)]
         self.f3 = [n(N0, N1) for _ in range(3)]
         self.g3 = [n(N0, N1) for _ in range(3)]
-        self.dpdx, self.dpdz = n(N0, N1), n(N0, N1)
+        self.dpdx = n(N0, N1)
+        self.rest3 = [n(N0, N1) for _ in range(3)]
         # transforms: D x D arrays may have odd widths (3073): plain allocations, only the DCT kernels touch them
         z = lambda *s: torch.zeros(s, dtype=torch.float64, device=self.dev)
         self.X8 = [FastStepper._new(self, D0, N1) for _ in range(8)]
@@ -89,6 +91,7 @@ class PassStepper(FastStepper):
         cF, dF = dict(zip(names, self.c3)), dict(zip(names, self.d3))
         eF, fF, gF = dict(zip(names, self.e3)), dict(zip(names, self.f3)), dict(zip(names, self.g3))
         zF, conv = dict(zip(names, self.z3)), dict(zip(names, self.conv))
+        rest = dict(zip(names, self.rest3))
         xb = {k: fld[k].xs[0] for k in names}
         yb = {k: fld[k].xs[1] for k in names}
         xbP, ybP = ns.P.xs[0], ns.P.xs[1]
@@ -106,12 +109,21 @@ class PassStepper(FastStepper):
             L.job(M1).load(F[k]).stencil(xb[k]).store(cF[k]).diff(sx).store(dF[k])
         L.job(N1).load(pres).diff(sx).store(self.dpdx)
         add(L)
-        # ---- PY2
+        # ---- PY2: y stencils / derivatives of the 8 arrays to transform, and everything of the right-hand sides that
+        # does not need the convective term (row passes run at ~1.6x the bandwidth of column passes:
+        # tools/bench_pass.py): rest_F = Sy Sx F + explicit terms
         L = PS.PassLaunch(PS.ROW, N1, self.tables)
         for k in names:
-            L.job(N0).load(cF[k]).stencil(yb[k]).store(eF[k]).diff(sz).store(gF[k])
+            p = L.job(N0).load(cF[k]).stencil(yb[k])
+            if k != "T":
+                p.store(eF[k])
+            p.diff(sz).store(gF[k])
             L.job(N0).load(dF[k]).stencil(yb[k]).store(fF[k])
-        L.job(N0).load(pres).diff(sz).store(self.dpdz)
+        st = {k: self.tables.stencil_elem(yb[k]) for k in names}
+        L.job(N0).load(cF["U"]).stencil(yb["U"]).axpy(-dt * a, self.dpdx).store(rest["U"])
+        L.job(N0).load(pres).diff(sz).scale(-dt * a).axpy(1.0, cF["V"], stencil=st["V"]) \
+            .axpy(dt * a, cF["T"], stencil=st["T"]).axpy(dt * a, self.tbc_cheby).store(rest["V"])
+        L.job(N0).load(cF["T"]).stencil(yb["T"]).axpy(dt * a * ns.kappa, self.dTbcdz2).store(rest["T"])
         add(L)
         # ---- transforms and products (both convective terms of the stage merged: ub = b u + c u_old)
         new, old = self.uw[rk % 2], self.uw[(rk + 1) % 2]
@@ -128,15 +140,11 @@ class PassStepper(FastStepper):
                   _ptr(dxU), _ptr(dzU), _ptr(dxV), _ptr(dzV), _ptr(dxT), _ptr(dzT), _ptr(self.dTbcdz1))
         self._dct(calls, self.plan1, ops.FWD, 1, [dxU, dxV, dxT], [f[:, : N1] for f in self.F3])
         self._dct(calls, self.plan0, ops.FWD, 0, [f[:, : N1] for f in self.F3], [cv[: N0] for cv in self.conv])
-        # ---- PX3: z = Ax^-1 Bx (Sy Sx F + rhs)
+        # ---- PX3: z = Ax^-1 Bx (rest - dt conv)
         L = PS.PassLaunch(PS.COL, N0, self.tables)
-        p = L.job(N1).lincomb([(1.0, eF["U"]), (-dt * a, self.dpdx), (-dt, conv["U"])])
-        p.band(solver["U"].plan_for_rhs[0].band).fdma(solver["U"].plan_for_lhs[0]).store(zF["U"])
-        p = L.job(N1).lincomb([(1.0, eF["V"]), (-dt * a, self.dpdz), (-dt, conv["V"]), (dt * a, eF["T"]),
-                               (dt * a, self.tbc_cheby)])
-        p.band(solver["V"].plan_for_rhs[0].band).fdma(solver["V"].plan_for_lhs[0]).store(zF["V"])
-        p = L.job(N1).lincomb([(1.0, eF["T"]), (-dt, conv["T"]), (dt * a * ns.kappa, self.dTbcdz2)])
-        p.band(solver["T"].plan_for_rhs[0].band).fdma(solver["T"].plan_for_lhs[0]).store(zF["T"])
+        for k in names:
+            L.job(N1).lincomb([(1.0, rest[k]), (-dt, conv[k])]).band(solver[k].plan_for_rhs[0].band) \
+                .fdma(solver[k].plan_for_lhs[0]).store(zF[k])
         add(L)
         # ---- PY4: F* = Ay^-1 By z; y parts of the divergence
         L = PS.PassLaunch(PS.ROW, N1, self.tables)
