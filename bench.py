@@ -43,6 +43,12 @@ METRIC = "rbc2d_fp64_timesteps_per_sec"
 UNIT = "steps/s"
 
 
+def base_config(args, cfg):
+    """The keys both arms (--impl b200 / reference) report under "config"."""
+    return {"workload": args.workload, "shape": list(cfg["shape"]), "integrator": cfg["integrator"],
+            "dealias": cfg["dealias"], "ra": cfg["ra"], "dt": cfg["dt"], "stages_per_step": 3 if cfg["integrator"] == "rk3" else 1}
+
+
 def init_state(ns, shape, port=False):
     """Synthetic initial fields of SURVEY.md §8(d).1 (same seed as the golden fixtures)."""
     ns.set_velocity(m=1, n=1, amplitude=0.2)
@@ -116,40 +122,34 @@ def cpu_cores():
 
 
 def oracle_sample(cfg, full_steps):
-    """Times the CPU oracle (bit-identical port of the reference's NumPy/SciPy/Fortran path).
-    full_steps > 0: that many complete RK3 steps.  full_steps == 0: ONLY the first RK3 stage of
-    one step (bounded sample); the step rate is extrapolated with the reference's own primitive
-    count per stage (22 : 40 : 40 1-D transforms)."""
+    """Times `full_steps` complete time steps of the CPU oracle (bit-identical port of the reference's
+    NumPy/SciPy/Fortran path) after its setup; the sample is measured, not extrapolated."""
     from oracle import pypde_port as P
+    try:        # torchrun / the image may pin BLAS to one thread: the two dense products get all host cores
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=cpu_cores())
+    except Exception:
+        pass
     t0 = time.perf_counter()
     o = P.RBC2D(**cfg)
     init_state(o, cfg["shape"], port=True)
     setup = time.perf_counter() - t0
-    if full_steps > 0:
-        t0 = time.perf_counter()
-        for _ in range(full_steps):
-            o.update()
-        dt = (time.perf_counter() - t0) / full_steps
-        return 1.0 / dt, setup, "%d full RK3 step(s) of %dx%d" % (full_steps, *cfg["shape"])
-    saved = o.nstage
-    o.nstage = 1                       # run stage 1 only (a, b, c of RK3 stage 1)
     t0 = time.perf_counter()
-    o.update()
-    dt = time.perf_counter() - t0
-    o.nstage = saved
-    factor = 102.0 / 22.0 if cfg["integrator"] == "rk3" else 1.0
-    return 1.0 / (dt * factor), setup, ("stage 1 of one RK3 step of %dx%d (%.1f s), step time = stage-1 time x %.2f "
-                                        "(reference's 1-D transform count per stage 22:40:40)"
-                                        % (*cfg["shape"], dt, factor))
+    for _ in range(full_steps):
+        o.update()
+    dt = (time.perf_counter() - t0) / full_steps
+    return 1.0 / dt, setup, "%d full %s step(s) of %dx%d, %.2f s each (no warm-up step)" % (
+        full_steps, cfg["integrator"].upper(), *cfg["shape"], dt)
 
 
 def run_reference(args, cfg):
     """--impl reference: the reference's CPU path.  /root/reference does not exist on the GPU box
-    and its Fortran cannot be built (no gfortran): the oracle port stands in (kind = "port")."""
+    and its Fortran cannot be built (no gfortran): the oracle port stands in (kind = "port").
+    At least 3 timed steps (2048^2: ~55 s each on 16 cores) after one warm-up step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    budget = float(os.environ.get("PDE_BENCH_CPU_BUDGET_S", "150"))
+    budget = float(os.environ.get("PDE_BENCH_CPU_BUDGET_S", "300"))
     try:        # torchrun exports OMP_NUM_THREADS=1: give the two dense BLAS products all host cores back
         from threadpoolctl import threadpool_limits
         threadpool_limits(limits=cpu_cores())
@@ -158,16 +158,12 @@ def run_reference(args, cfg):
     from oracle import pypde_port as P
     o = P.RBC2D(**cfg)
     init_state(o, cfg["shape"], port=True)
-    # warm-up + cost probe: stage 1 of one step (22 of the 102 1-D transforms of an RK3 step)
-    nst = o.nstage
-    o.nstage = 1
     t0 = time.perf_counter()
-    o.update()
-    probe = (time.perf_counter() - t0) * (102.0 / 22.0 if nst == 3 else 1.0)
-    o.nstage = nst
+    o.update()                       # warm-up + cost probe
+    probe = time.perf_counter() - t0
     warm = 1
-    steps = max(1, min(args.steps, int(budget / max(probe, 1e-9))))
-    while warm < args.warmup and probe * (warm + steps) < budget:
+    steps = max(min(3, args.steps), min(args.steps, int(budget / max(probe, 1e-9)) - 1))
+    while warm < args.warmup and probe * (warm + 1 + steps) < budget:
         o.update()
         warm += 1
     t0 = time.perf_counter()
@@ -175,14 +171,13 @@ def run_reference(args, cfg):
         o.update()
     dt = (time.perf_counter() - t0) / steps
     val = 1.0 / dt
-    sample = "%d full RK3 step(s) of %dx%d after %d warm-up (requested %d/%d, clamped to a %.0f s budget)" % (
+    sample = "%d full step(s) of %dx%d after %d warm-up (requested %d/%d, clamped to a %.0f s budget, never below 3 timed steps)" % (
         steps, *cfg["shape"], warm, args.steps, args.warmup, budget)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "shape": list(cfg["shape"]), "integrator": cfg["integrator"],
-                   "dealias": cfg["dealias"], "ra": cfg["ra"], "dt": cfg["dt"]},
+        "config": base_config(args, cfg),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cpu_cores(), "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -192,7 +187,7 @@ def run_reference(args, cfg):
 # --------------------------------------------------------------------------- GPU arm
 class OpTimer:
     """CUDA-event timer around every C-ABI call of one (eager) time step: wraps the prebuilt launch
-    lists of the batched stepper."""
+    lists of the stepper.  Events are recorded on the stream the kernels are launched on."""
 
     def __init__(self):
         self.records = []
@@ -203,31 +198,28 @@ class OpTimer:
         fs = ns._fast
         st = _cabi.stream()
         for rk in range(ns.nstage):
-            npass = 0
-            for fn, args in fs.stage_calls[rk].calls:
+            lst = fs.stage_calls[rk]
+            labels = getattr(lst, "labels", None) or [getattr(fn, "__name__", "call") for fn, _ in lst.calls]
+            for (fn, args), name in zip(lst.calls, labels):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 _cabi.check(fn(*args, st))
                 e1.record()
-                name = getattr(fn, "__name__", "call")
-                if name == "pde_pass_run":
-                    npass += 1
-                    name = "pde_pass_run[P%s%d]" % ("Y" if args[0] else "X", npass)
-                self.records.append((name, args, e0, e1))
+                self.records.append((name, getattr(fn, "__name__", "call"), args, e0, e1))
         torch.cuda.synchronize()
 
     def summary(self):
         out = {}
-        for name, a, e0, e1 in self.records:
+        for name, fname, a, e0, e1 in self.records:
             key = name
             work = None
-            if name == "pde_sweep":
+            if fname == "pde_sweep":
                 key = "pde_sweep[%s,axis%d]" % (["diff", "tdma_fwd", "tdma_bwd", "fdma_fwd", "fdma_bwd", "twodma"][a[0]], a[1])
-            if name == "pde_dct1_multi":
+            if fname == "pde_dct1_multi":
                 key = "pde_dct1_multi[axis%d]" % a[10]
-                # algorithmic bytes: 8 read + 8 written per element of the longer side
-                work = 16.0 * a[2] * max(a[5], a[8]) * a[9]
-            if name == "pde_gemm_f64":
+                # algorithmic bytes: every input element read once (n_in), every output element written once (n_out)
+                work = 8.0 * a[2] * (a[5] + a[8]) * a[9]
+            if fname == "pde_gemm_f64":
                 work = 2.0 * a[7] * a[8] * a[9]
             d = out.setdefault(key, {"ms": 0.0, "launches": 0, "work": 0.0})
             d["ms"] += e0.elapsed_time(e1)
@@ -383,7 +375,7 @@ def run_gpu(args, cfg):
         init_nccl(local)
         # Capturing the NCCL transposes in the CUDA graph works (rbc512 x2: 2.74 vs 3.03 ms/step) but the
         # process then hung in teardown on this stack, so the multi-GPU step is launched eagerly.
-        if os.environ.get("PDE_SLAB_GRAPH", "0") != "1":
+        if os.environ.get("PDE_SLAB_GRAPH", "1") != "1":
             args.no_graph = True
     from pypde_b200 import _cabi
     from pypde_b200.navier import rbc2d
@@ -476,16 +468,12 @@ def run_gpu(args, cfg):
     dct_work = sum(v["work"] for k, v in ops_ms.items() if k.startswith("pde_dct1"))
     dct_launches = sum(v["launches"] for k, v in ops_ms.items() if k.startswith("pde_dct1"))
     gemm = ops_ms.get("pde_gemm_f64", {"ms": 0.0, "work": 0.0, "launches": 1})
-    roof_dct = {"kernel": "k_dct_fft (shared-memory FFT DCT-I, all batched transforms of the step)", "bound": "hbm",
+    roof_dct = {"kernel": "k_dct_fft_t (shared-memory FFT DCT-I, all batched transforms of the step)", "bound": "hbm",
                 "achieved": dct_work / (dct_ms * 1e-3) / 1e9 if dct_ms else None, "peak": peaks.get("hbm_gbs"),
                 "unit": "GB/s",
-                "traffic": 548850000 if (tuple(cfg["shape"]) == (2048, 2048) and not slab) else None,
-                "traffic_note": "(rbc2048 on one GPU only) dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the four DCT "
-                                "launches of one stage (ncu --set full of an eager rbc2048 stage, "
-                                "profiles/r01_ncu_stage_final.csv: 8 backward arrays along axis 0 634 MB, 8 backward "
-                                "along axis 1 982 MB, 3 forward along axis 1 352 MB, 3 forward along axis 0 227 MB) "
-                                "against 692 MB algorithmic per launch: below it because part of each array is still "
-                                "in the 126 MB L2 from the producing kernel; no re-reads",
+                "traffic": None,
+                "traffic_note": "not captured in this run (ncu --set full of the stage: profiles/); algorithmic bytes = "
+                                "8 (n_in + n_out) batch per array: every input element read once, every output element written once",
                 "peak_source": peak_src, "launches_per_step": dct_launches,
                 "avg_launch_ms": dct_ms / max(dct_launches, 1), "share_of_step": dct_ms / step_ms_instr,
                 "algorithmic_bytes_per_launch": dct_work / max(dct_launches, 1)}
@@ -500,11 +488,41 @@ def run_gpu(args, cfg):
     roof = roof_dct if dct_ms >= gemm["ms"] else roof_gemm
     roof_other = roof_gemm if roof is roof_dct else roof_dct
 
+    # ---- multi-GPU: the slab-decomposed state against the single-GPU stepper, outside the timed region ----
+    parity = None
+    if slab:
+        psteps = 2
+        chk = rbc2d.NavierStokes(graph=False, slab=True, **cfg)
+        init_state(chk, cfg["shape"])
+        for _ in range(psteps):
+            chk.update()
+        chk.sync_fields()
+        torch.cuda.synchronize()
+        if hasattr(chk._fast, "check"):
+            chk._fast.check()
+        if rank == 0:
+            one = rbc2d.NavierStokes(graph=False, slab=False, **cfg)
+            init_state(one, cfg["shape"])
+            for _ in range(psteps):
+                one.update()
+            torch.cuda.synchronize()
+            errs = {}
+            for k, a, b in (("T", chk.T.vhat, one.T.vhat), ("U", chk.U.vhat, one.U.vhat), ("V", chk.V.vhat, one.V.vhat),
+                            ("pres", chk.pres.vhat, one.pres.vhat)):
+                errs[k] = float(torch.linalg.norm(a - b) / torch.linalg.norm(b))
+            parity = {"steps": psteps, "rel_l2": errs, "max": max(errs.values()),
+                      "note": "slab-decomposed state (gathered) vs the single-GPU stepper on rank 0, same initial state; the "
+                              "reference's own step moves by 3e-11 (U, V, pres) at 2048^2 when its input changes by half an ulp "
+                              "(tests/test_gpu_large.py), so two roundings of the same step agree to that level"}
+            del one
+        chk.close()
+        del chk
+
     # ---- CPU baseline: bounded sample of the same workload on rank 0 -----------------------
     cpu = None
     if not args.no_cpu_baseline and not slab and rank == 0:
         big = cfg["shape"][0] * cfg["shape"][1] > 600 * 600
-        v, cpu_setup, sample = oracle_sample(cfg, 0 if big else 2)
+        v, cpu_setup, sample = oracle_sample(cfg, 1 if big else 3)
         cpu = {"value": v, "unit": UNIT, "cores": cpu_cores(), "kind": "port", "sample": sample,
                "setup_s": cpu_setup}
 
@@ -514,17 +532,24 @@ def run_gpu(args, cfg):
     stage_bytes = 8 * (31 * M * M + 18 * M * N + 5 * N * N + 12 * D * M + 6 * D * N + D * D)
     stage_flop = 2.0 * M * N * M + 2.0 * M ** 3
     nst = ns.nstage
+    hbm = peaks.get("hbm_gbs", 6650.0) * 1e9 * world            # N GPUs: N x the peaks
+    fl = fp64_peak * 1e12 * world
+    t_step = ms / args.steps * 1e-3
+    kern = {k: round(v["ms"], 4) for k, v in sorted(ops_ms.items(), key=lambda kv: -kv[1]["ms"])}
+    config = base_config(args, cfg)
+    config.update({
+        "parallelism": ("slab x%d: peer-memory row passes (loads / stores over NVLink), device-side barriers, no NCCL on the "
+                        "data path" % world) if slab else "single GPU",
+        "stepper": type(ns._fast).__name__,
+        "l2": "state + work arrays exceed the 126 MB L2 (no flush needed)" if N >= 1024
+        else "working set fits L2 (small-grid regime, by design of the workload)",
+        "finite": finite, "setup_s": setup_s, "cuda_graph": not args.no_graph,
+        "dealias_grid": list(ns.deriv_field.dealias.shape_physical) if cfg["dealias"] else None})
     line = {
         "metric": METRIC, "value": args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "shape": list(cfg["shape"]), "integrator": cfg["integrator"],
-                   "dealias": cfg["dealias"], "ra": cfg["ra"], "dt": cfg["dt"], "stages_per_step": nst,
-                   "parallelism": ("slab x%d, %d all-to-all transposes per step" % (world, 10 * nst)) if slab else "single GPU",
-                   "l2": "state + work arrays exceed the 126 MB L2 (no flush needed)" if N >= 1024
-                   else "working set fits L2 (small-grid regime, by design of the workload)",
-                   "finite": finite, "setup_s": setup_s, "cuda_graph": not args.no_graph,
-                   "dealias_grid": list(ns.deriv_field.dealias.shape_physical) if cfg["dealias"] else None},
+        "config": config,
         "clocks": clocks,
         "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
@@ -533,20 +558,27 @@ def run_gpu(args, cfg):
         "roofline": roof,
         "roofline_second": roof_other,
         "step_model": {"algorithmic_bytes_per_step": stage_bytes * nst, "dense_flop_per_step": stage_flop * nst,
-                       "hbm_fraction": (stage_bytes * nst / (peaks.get("hbm_gbs", 6650.0) * 1e9)) / (ms / args.steps * 1e-3),
-                       "combined_fraction": (stage_bytes * nst / (peaks.get("hbm_gbs", 6650.0) * 1e9)
-                                             + stage_flop * nst / (fp64_peak * 1e12)) / (ms / args.steps * 1e-3),
-                       "fp64_peak_tflops": fp64_peak, "hbm_peak_gbs": peaks.get("hbm_gbs")},
-        "kernel_ms_per_step": {k: round(v["ms"], 4) for k, v in sorted(ops_ms.items(), key=lambda kv: -kv[1]["ms"])},
+                       "hbm_fraction": (stage_bytes * nst / hbm) / t_step,
+                       "combined_fraction": (stage_bytes * nst / hbm + stage_flop * nst / fl) / t_step,
+                       "fp64_peak_tflops_per_gpu": fp64_peak, "hbm_peak_gbs_per_gpu": peaks.get("hbm_gbs"), "n_gpus": world,
+                       "note": "SURVEY.md 8(d) axis-pass model; peaks are per GPU x n_gpus"},
+        "kernel_ms_per_step": kern,
         "cpu_baseline": cpu,
     }
     if slab:
-        tms = sum(v for k, v in line["kernel_ms_per_step"].items() if k.startswith("slab_transpose"))
+        # exchange = the kernels that exist only because the grid is distributed: the two-instruction row passes that move the
+        # inputs / outputs of the transforms and projections, and the device-side barriers; the other transposes are the
+        # loads / stores of row passes that also compute (PY2, PY4, PY7)
+        tms = sum(v for k, v in kern.items() if k.startswith("exchange") or k == "peer_barrier" or k.startswith("slab_transpose"))
         line["transpose_ms_per_step"] = tms
-        line["transpose_bytes_sent_per_rank_per_step"] = ns._fast.comm.bytes_sent // max(1, ns._fast.comm.calls // (10 * nst))
+        line["transpose_note"] = "exchange-only passes + device barriers of rank 0 (eager, event-timed); the pulls / pushes fused " \
+                                 "into the computing row passes are inside pass[PY*]"
+        line["parity_vs_single_gpu"] = parity["max"] if parity else None
+        line["parity_detail"] = parity
     if rank == 0:
         print(json.dumps(line))
     if slab:
+        ns.close()
         dist.destroy_process_group()
 
 

@@ -39,10 +39,12 @@ class _Calls:
 
     def __init__(self):
         self.calls = []
+        self.labels = []    # one name per call (bench.py's per-kernel timing)
         self.keep = []      # ctypes arrays / tensors that must stay alive
 
-    def add(self, fn, *args):
+    def add(self, fn, *args, label=None):
         self.calls.append((fn, args))
+        self.labels.append(label or getattr(fn, "__name__", "call"))
 
     def run(self):
         st = C.stream()

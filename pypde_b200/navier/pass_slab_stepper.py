@@ -147,15 +147,18 @@ class PassSlabStepper(FastStepper):
         state = {k: xl("S" + k, M0, M1c) for k in names}
         pres = xl("pres", N0, W)
 
-        def add(L):
+        npass = [0]
+
+        def add(L, label=None):
             L.finalize()
             calls.keep.append(L)
             fn, args = L.args()
-            calls.add(fn, *args)
+            npass[0] += 1
+            calls.add(fn, *args, label=label or "pass[P%s%d]" % ("Y" if L.layout else "X", npass[0]))
 
         def barrier():
             fn, args = self.mem.barrier_args()
-            calls.add(fn, *args)
+            calls.add(fn, *args, label="peer_barrier")
 
         # ---- PX1 (local): F -> Sx F, dx Sx F / sx; pres -> dpdx
         L = PS.PassLaunch(PS.COL, N0, self.tables)
@@ -180,7 +183,7 @@ class PassSlabStepper(FastStepper):
         L = PS.PassLaunch(PS.ROW, N1, self.tables)
         for k in range(8):
             L.job(D0r, d0).load(xr("X8_%d" % k, N1, d0)).store(self.Y8[k])
-        add(L)
+        add(L, "exchange[pull 8 (D x N)]")
         # ---- backward y-DCT, products, forward y-DCT (local rows)
         new, old = self.uw[rk % 2], self.uw[(rk + 1) % 2]
         dxU, dxV, dxT, dzU, dzV, dzT = self.phys
@@ -193,7 +196,7 @@ class PassSlabStepper(FastStepper):
         L = PS.PassLaunch(PS.ROW, N1, self.tables)
         for k in range(3):
             L.job(D0r, d0).load(self.F3y[k]).store(xr("F3_%d" % k, N1, d0))
-        add(L)
+        add(L, "exchange[push 3 (D x N)]")
         barrier()
         # ---- forward x-DCT (local), PX3: z = Ax^-1 Bx (Sy Sx F + rhs)
         conv = {k: xl("conv" + k, N0, W) for k in names}
@@ -234,12 +237,12 @@ class PassSlabStepper(FastStepper):
         Hy, Qy = sp.plan_for_rhs[1].dense, sp.plan_for_lhs[1].dense
         L = PS.PassLaunch(PS.ROW, N1, self.tables)
         L.job(M0r, r0).load(xr("q", N1, r0)).store(self.qY)
-        add(L)
+        add(L, "exchange[pull q]")
         calls.add(Lb.pde_gemm_f64, 1, _ptr(self.qY), _ld(self.qY), _ptr(Hy), _ld(Hy), _ptr(self.RY), _ld(self.RY),
                   M0r, M1, N1)
         L = PS.PassLaunch(PS.ROW, N1, self.tables)
         L.job(M0r, r0).load(self.RY).store(xr("R", M1, r0))
-        add(L)
+        add(L, "exchange[push R]")
         barrier()
         # ---- PX6 (local): per-column Poisson solves
         Rx = xl("R", M0, M1c)
@@ -250,7 +253,7 @@ class PassSlabStepper(FastStepper):
         # ---- P = W Qy^T on my rows; PY7: P[0,0] = 0, e1 = Sy P, bU = Gy e1, bV = Gy dz e1 / sz (pushed)
         L = PS.PassLaunch(PS.ROW, N1, self.tables)
         L.job(M0r, r0).load(xr("R", M1, r0)).store(self.WY)
-        add(L)
+        add(L, "exchange[pull W]")
         calls.add(Lb.pde_gemm_f64, 1, _ptr(self.WY), _ld(self.WY), _ptr(Qy), _ld(Qy), _ptr(self.PY), _ld(self.PY),
                   M0r, M1, M1)
         Py = self.PY[:M0r]

@@ -97,11 +97,14 @@ class PassStepper(FastStepper):
         xbP, ybP = ns.P.xs[0], ns.P.xs[1]
         solver = {"U": ns.solver_U[rk], "V": ns.solver_V[rk], "T": ns.solver_T[rk]}
 
-        def add(L):
+        npass = [0]
+
+        def add(L, label=None):
             L.finalize()
             calls.keep.append(L)
             fn, args = L.args()
-            calls.add(fn, *args)
+            npass[0] += 1
+            calls.add(fn, *args, label=label or "pass[P%s%d]" % ("Y" if L.layout else "X", npass[0]))
 
         # ---- PX1
         L = PS.PassLaunch(PS.COL, N0, self.tables)
