@@ -233,9 +233,25 @@ int pde_conv_products(long n, double b, double c, const double *u, const double 
                       const double *w_old, double *dxU, const double *dzU, double *dxV, const double *dzV,
                       double *dxT, const double *dzT, const double *dTbc, void *stream);
 
+/* The same products for `nmembers` independent runs whose arrays lie `stride` elements apart (ensemble of
+ * equal grids; dTbc is shared). */
+int pde_conv_products_members(long n, int nmembers, long stride, double b, double c, const double *u, const double *w,
+                              const double *u_old, const double *w_old, double *dxU, const double *dzU, double *dxV,
+                              const double *dzV, double *dxT, const double *dzT, const double *dTbc, void *stream);
+
 /* pde_dct1 on several arrays of identical shape */
 int pde_dct1_multi(pde_dct_plan_t plan, int mode, int njobs, const double *const *x, long ldx, int n_in,
                    double *const *y, long ldy, int n_out, int batch, int axis, void *stream);
+
+/* Batched forms for ensembles of small grids (one launch for all members): operands come from DEVICE arrays
+ * of `nbatch` pointers.  pde_dct1_batched needs a plan of the dense-matrix kind (pde_dct_plan_algo == 1);
+ * pde_gemm_f64_batched takes each of A / B either shared (plain pointer) or per problem (device pointer array).
+ * aligned != 0: the caller guarantees 16-byte aligned operands. */
+int pde_dct1_batched(pde_dct_plan_t plan, int mode, int nbatch, const double *const *dev_x, long ldx, int n_in,
+                     double *const *dev_y, long ldy, int n_out, int batch, int axis, int aligned, void *stream);
+int pde_gemm_f64_batched(int transB, const double *A, const double *const *dev_A, long lda, const double *B,
+                         const double *const *dev_B, long ldb, double *const *dev_C, long ldc, int m, int n, int k,
+                         int nbatch, int aligned, void *stream);
 
 /* ---- slab decomposition: pack / unpack of a bundle for the all-to-all transposes -------
  * bundle : (rows, K*cols) row-major, K arrays side by side (array k = columns k*cols .. k*cols+cols-1)

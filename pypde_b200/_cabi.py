@@ -99,6 +99,12 @@ SIGNATURES.update({
     "pde_slab_repack": (_c_int, [_c_int, _c_dp, _c_dp, _c_int, _c_int, _c_int, _c_int, ctypes.POINTER(_c_int),
                                  ctypes.c_void_p]),
     "pde_conv_products": (_c_int, [_c_long, ctypes.c_double, ctypes.c_double] + [_c_dp] * 11 + [ctypes.c_void_p]),
+    "pde_conv_products_members": (_c_int, [_c_long, _c_int, _c_long, ctypes.c_double, ctypes.c_double] + [_c_dp] * 11
+                                  + [ctypes.c_void_p]),
+    "pde_dct1_batched": (_c_int, [ctypes.c_void_p, _c_int, _c_int, ctypes.c_void_p, _c_long, _c_int, ctypes.c_void_p,
+                                  _c_long, _c_int, _c_int, _c_int, _c_int, ctypes.c_void_p]),
+    "pde_gemm_f64_batched": (_c_int, [_c_int, _c_dp, ctypes.c_void_p, _c_long, _c_dp, ctypes.c_void_p, _c_long,
+                                      ctypes.c_void_p, _c_long, _c_int, _c_int, _c_int, _c_int, _c_int, ctypes.c_void_p]),
     "pde_dct1_multi": (_c_int, [ctypes.c_void_p, _c_int, _c_int, ctypes.POINTER(ctypes.c_void_p), _c_long, _c_int,
                                 ctypes.POINTER(ctypes.c_void_p), _c_long, _c_int, _c_int, _c_int, ctypes.c_void_p]),
 })

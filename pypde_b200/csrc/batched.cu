@@ -274,6 +274,31 @@ __global__ void k_conv_products(long n, double b, double c, const double *__rest
     }
 }
 
+// the same products for `gridDim.y` members whose arrays lie `stride` elements apart (dTbc is shared)
+__global__ void k_conv_products_members(long n, long stride, double b, double c, const double *__restrict__ u,
+                                        const double *__restrict__ w, const double *__restrict__ uo,
+                                        const double *__restrict__ wo, double *dxU, const double *__restrict__ dzU,
+                                        double *dxV, const double *__restrict__ dzV, double *dxT,
+                                        const double *__restrict__ dzT, const double *__restrict__ dTbc)
+{
+    const long o = (long)blockIdx.y * stride;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        double ub = u[o + i], wb = w[o + i];
+        if (uo != nullptr) {
+            ub = b * ub + c * uo[o + i];
+            wb = b * wb + c * wo[o + i];
+        } else if (b != 1.0) {
+            ub = b * ub;
+            wb = b * wb;
+        }
+        dxU[o + i] = dxU[o + i] * ub + dzU[o + i] * wb;
+        dxV[o + i] = dxV[o + i] * ub + dzV[o + i] * wb;
+        double t = dxT[o + i] * ub + dzT[o + i] * wb;
+        if (dTbc != nullptr) t = t + wb * dTbc[i];
+        dxT[o + i] = t;
+    }
+}
+
 struct SlabOff {
     int n;
     int off[17];
@@ -469,6 +494,20 @@ int pde_conv_products(long n, double b, double c, const double *u, const double 
     k_conv_products<<<grid, 256, 0, as_stream(stream)>>>(n, b, c, u, w, u_old, w_old, dxU, dzU, dxV, dzV, dxT,
                                                          dzT, dTbc);
     return after_launch("pde_conv_products");
+}
+
+int pde_conv_products_members(long n, int nmembers, long stride, double b, double c, const double *u, const double *w,
+                              const double *u_old, const double *w_old, double *dxU, const double *dzU, double *dxV,
+                              const double *dzV, double *dxT, const double *dzT, const double *dTbc, void *stream)
+{
+    PDE_REQUIRE(u && w && dxU && dzU && dxV && dzV && dxT && dzT, "null pointer");
+    PDE_REQUIRE((u_old == nullptr) == (w_old == nullptr), "u_old and w_old go together");
+    PDE_REQUIRE(nmembers >= 1 && nmembers <= 65535 && stride >= n, "members / stride");
+    if (n <= 0) return PDE_OK;
+    const int gx = (int)((n + 255) / 256 < 148 * 4 ? (n + 255) / 256 : 148 * 4);
+    k_conv_products_members<<<dim3(gx, nmembers), 256, 0, as_stream(stream)>>>(n, stride, b, c, u, w, u_old, w_old, dxU,
+                                                                              dzU, dxV, dzV, dxT, dzT, dTbc);
+    return after_launch("pde_conv_products_members");
 }
 
 }  // extern "C"

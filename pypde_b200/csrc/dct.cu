@@ -16,6 +16,9 @@
 
 namespace pde {
 
+int gemm_f64_batched(bool transB, const double *A, const double *const *Aarr, long lda, const double *B,
+                     const double *const *Barr, long ldb, double *const *Carr, long ldc, int m, int n, int k,
+                     int nbatch, bool vec, cudaStream_t st);
 int gemm_f64(bool transB, const double *A, long lda, const double *B, long ldb, double *C, long ldc, int m,
              int n, int k, cudaStream_t st);
 
@@ -153,6 +156,28 @@ int pde_dct1_multi(pde_dct_plan_t p, int mode, int njobs, const double *const *x
             rc = gemm_f64(true, x[j], ldx, p->mat[mode], p->ldm, y[j], ldy, batch, n_out, n_in, st);
     }
     return rc;
+}
+
+int pde_dct1_batched(pde_dct_plan_t p, int mode, int nbatch, const double *const *dev_x, long ldx, int n_in,
+                     double *const *dev_y, long ldy, int n_out, int batch, int axis, int aligned, void *stream)
+{
+    PDE_REQUIRE(p && dev_x && dev_y, "null pointer");
+    PDE_REQUIRE(mode >= 0 && mode <= 2 && (axis == 0 || axis == 1) && nbatch >= 1, "arguments");
+    PDE_REQUIRE(n_in >= 1 && n_in <= p->L && n_out >= 1 && n_out <= p->L, "n_in / n_out in 1..L");
+    if (p->algo != 1) {
+        set_error("pde_dct1_batched: plan of length %d uses the FFT path; the batched form is the dense-matrix path", p->L);
+        return PDE_ERR_UNSUPPORTED;
+    }
+    if (batch <= 0) return PDE_OK;
+    int rc = build_dense(p, mode);
+    if (rc != PDE_OK) return rc;
+    const bool vec = aligned && ldx % 2 == 0 && ldy % 2 == 0 && p->ldm % 2 == 0;
+    if (axis == 0)   // Y(n_out x batch) = Mat(n_out x n_in) X(n_in x batch)
+        return gemm_f64_batched(false, p->mat[mode], nullptr, p->ldm, nullptr, dev_x, ldx, dev_y, ldy, n_out, batch, n_in,
+                                nbatch, vec, as_stream(stream));
+    // Y(batch x n_out) = X(batch x n_in) Mat(n_out x n_in)^T
+    return gemm_f64_batched(true, nullptr, dev_x, ldx, p->mat[mode], nullptr, p->ldm, dev_y, ldy, batch, n_out, n_in, nbatch,
+                            vec, as_stream(stream));
 }
 
 int pde_dct1(pde_dct_plan_t p, int mode, const double *x, long ldx, int n_in, double *y, long ldy,

@@ -105,11 +105,23 @@ __device__ __forceinline__ void load_tile_nmajor(double *sm, const double *g, lo
     }
 }
 
+// batched form: blockIdx.z picks the operands of one problem out of DEVICE pointer arrays (a null array = the
+// operand is shared by all problems): the ensemble runs the dense DCT / projection products of all its members
+// in one launch
+struct GemmBatch {
+    const double *const *A;
+    const double *const *B;
+    double *const *C;
+};
+
 template <bool TB, bool VEC, int MI, int NI, int WN>
 __global__ void __launch_bounds__(256, 2)
 k_gemm_f64(const double *__restrict__ A, long lda, const double *__restrict__ B, long ldb,
-           double *__restrict__ C, long ldc, int M, int N, int K)
+           double *__restrict__ C, long ldc, int M, int N, int K, GemmBatch bt)
 {
+    if (bt.A) A = bt.A[blockIdx.z];
+    if (bt.B) B = bt.B[blockIdx.z];
+    if (bt.C) C = bt.C[blockIdx.z];
     constexpr int WM = 8 / WN;
     constexpr int BM = WM * 8 * MI, BNT = WN * 8 * NI;
     static_assert(BM <= 128 && BNT <= BN, "tile exceeds the shared-memory layout");
@@ -190,7 +202,7 @@ static const GemmShape GEMM_SHAPES[] = {{128, 64}, {128, 56}, {128, 48}, {64, 64
 
 template <bool TB, bool VEC, int MI, int NI, int WN>
 static int gemm_launch(const double *A, long lda, const double *B, long ldb, double *C, long ldc, int m, int n,
-                       int k, cudaStream_t st)
+                       int k, cudaStream_t st, GemmBatch bt = GemmBatch{nullptr, nullptr, nullptr}, int nbatch = 1)
 {
     auto kern = k_gemm_f64<TB, VEC, MI, NI, WN>;
     static PerDeviceFlag attr;
@@ -199,21 +211,21 @@ static int gemm_launch(const double *A, long lda, const double *B, long ldb, dou
         attr.get() = true;
     }
     constexpr int BM = (8 / WN) * 8 * MI, BNT = WN * 8 * NI;
-    dim3 grid(ceil_div(n, BNT), ceil_div(m, BM));
-    kern<<<grid, 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, m, n, k);
+    dim3 grid(ceil_div(n, BNT), ceil_div(m, BM), nbatch);
+    kern<<<grid, 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, m, n, k, bt);
     return after_launch("pde_gemm_f64");
 }
 
 template <bool TB, bool VEC>
 static int gemm_shape(int shape, const double *A, long lda, const double *B, long ldb, double *C, long ldc, int m,
-                      int n, int k, cudaStream_t st)
+                      int n, int k, cudaStream_t st, GemmBatch bt = GemmBatch{nullptr, nullptr, nullptr}, int nbatch = 1)
 {
     switch (shape) {
-    case 0: return gemm_launch<TB, VEC, 4, 4, 2>(A, lda, B, ldb, C, ldc, m, n, k, st);   // 128 x 64
-    case 1: return gemm_launch<TB, VEC, 2, 7, 1>(A, lda, B, ldb, C, ldc, m, n, k, st);   // 128 x 56
-    case 2: return gemm_launch<TB, VEC, 2, 6, 1>(A, lda, B, ldb, C, ldc, m, n, k, st);   // 128 x 48
-    case 3: return gemm_launch<TB, VEC, 2, 4, 2>(A, lda, B, ldb, C, ldc, m, n, k, st);   // 64 x 64
-    default: return gemm_launch<TB, VEC, 1, 4, 2>(A, lda, B, ldb, C, ldc, m, n, k, st);  // 32 x 64
+    case 0: return gemm_launch<TB, VEC, 4, 4, 2>(A, lda, B, ldb, C, ldc, m, n, k, st, bt, nbatch);   // 128 x 64
+    case 1: return gemm_launch<TB, VEC, 2, 7, 1>(A, lda, B, ldb, C, ldc, m, n, k, st, bt, nbatch);   // 128 x 56
+    case 2: return gemm_launch<TB, VEC, 2, 6, 1>(A, lda, B, ldb, C, ldc, m, n, k, st, bt, nbatch);   // 128 x 48
+    case 3: return gemm_launch<TB, VEC, 2, 4, 2>(A, lda, B, ldb, C, ldc, m, n, k, st, bt, nbatch);   // 64 x 64
+    default: return gemm_launch<TB, VEC, 1, 4, 2>(A, lda, B, ldb, C, ldc, m, n, k, st, bt, nbatch);  // 32 x 64
     }
 }
 
@@ -253,7 +265,39 @@ int gemm_f64(bool transB, const double *A, long lda, const double *B, long ldb, 
                : gemm_shape<false, false>(shape, A, lda, B, ldb, C, ldc, m, n, k, st);
 }
 
+// nbatch problems of one shape; operands from device pointer arrays (null array: shared operand A / B).
+// `vec`: the caller guarantees 16-byte aligned operands with even leading dimensions.
+int gemm_f64_batched(bool transB, const double *A, const double *const *Aarr, long lda, const double *B,
+                     const double *const *Barr, long ldb, double *const *Carr, long ldc, int m, int n, int k,
+                     int nbatch, bool vec, cudaStream_t st)
+{
+    if (m <= 0 || n <= 0 || nbatch <= 0) return PDE_OK;
+    const long slots = 2L * sm_count();
+    int shape = 0;
+    if ((long)ceil_div(n, 64) * ceil_div(m, 64) * nbatch < slots) shape = 4;
+    else if ((long)ceil_div(n, 64) * ceil_div(m, 128) * nbatch < slots || m <= 64) shape = m <= 32 ? 4 : 3;
+    GemmBatch bt{Aarr, Barr, Carr};
+    if (transB) return vec ? gemm_shape<true, true>(shape, A, lda, B, ldb, nullptr, ldc, m, n, k, st, bt, nbatch)
+                           : gemm_shape<true, false>(shape, A, lda, B, ldb, nullptr, ldc, m, n, k, st, bt, nbatch);
+    return vec ? gemm_shape<false, true>(shape, A, lda, B, ldb, nullptr, ldc, m, n, k, st, bt, nbatch)
+               : gemm_shape<false, false>(shape, A, lda, B, ldb, nullptr, ldc, m, n, k, st, bt, nbatch);
+}
+
 }  // namespace pde
+
+extern "C" int pde_gemm_f64_batched(int transB, const double *A, const double *const *dev_A, long lda,
+                                    const double *B, const double *const *dev_B, long ldb, double *const *dev_C,
+                                    long ldc, int m, int n, int k, int nbatch, int aligned, void *stream)
+{
+    PDE_REQUIRE((A != nullptr) != (dev_A != nullptr), "exactly one of A / dev_A");
+    PDE_REQUIRE((B != nullptr) != (dev_B != nullptr), "exactly one of B / dev_B");
+    PDE_REQUIRE(dev_C != nullptr && k >= 1 && nbatch >= 1 && nbatch <= 65535, "arguments");
+    PDE_REQUIRE(lda >= k && ldc >= n && ldb >= (transB ? k : n), "leading dimensions");
+    const bool vec = aligned && (lda % 2 == 0) && (ldb % 2 == 0) && (ldc % 2 == 0) &&
+                     (!A || (uintptr_t)A % 16 == 0) && (!B || (uintptr_t)B % 16 == 0);
+    return pde::gemm_f64_batched(transB != 0, A, dev_A, lda, B, dev_B, ldb, dev_C, ldc, m, n, k, nbatch, vec,
+                                 pde::as_stream(stream));
+}
 
 extern "C" int pde_gemm_f64(int transB, const double *A, long lda, const double *B, long ldb, double *C,
                             long ldc, int m, int n, int k, void *stream)
