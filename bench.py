@@ -302,10 +302,17 @@ def run_ensemble(args):
     # launches: one eager member step counted through the library, times members and steps
     m0 = ens.members[0]
     _cabi.launch_count_reset()
-    for rk in range(m0.nstage):
-        m0._fast.stage_calls[rk].run()
-    torch.cuda.synchronize()
-    per_member = _cabi.launch_count()
+    if ens.batched:
+        ens._run_eager()                # one eager ensemble step: every launch carries all members
+        torch.cuda.synchronize()
+        launches_step = _cabi.launch_count()
+        per_member = launches_step / max(1, len(ens.members))
+    else:
+        for rk in range(m0.nstage):
+            m0._fast.stage_calls[rk].run()
+        torch.cuda.synchronize()
+        per_member = _cabi.launch_count()
+        launches_step = per_member * len(ens.members)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import pypde_port as P
@@ -328,7 +335,8 @@ def run_ensemble(args):
                        "l2": "one member's working set fits L2 (small-grid regime by design)", "finite": finite,
                        "setup_s": setup_s, "cuda_graph": True},
             "member_steps_per_sec": args.steps * ENSEMBLE["members"] / (ms * 1e-3),
-            "clocks": clocks, "gpu_launches": per_member * len(ens.members) * args.steps,
+            "clocks": clocks, "gpu_launches": int(launches_step * args.steps),
+            "gpu_launches_per_ensemble_step": int(launches_step), "batched": bool(ens.batched),
             "gpu_launches_per_member_step": per_member, "cpu_baseline": cpu}
     if rank == 0:
         print(json.dumps(line))

@@ -138,18 +138,18 @@ class TableCache:
         def make():
             s = base._tables_host()[0]
             return unit_table(shift2(s), lg)
-        return self.get((id(base), base.N, base.id, "S", lg), make)
+        return self.get((base.N, base.id, "S", lg), make)
 
     def stencil_elem(self, base):
         """element table st_i = s_{i-2} for AXPY with the STENCIL flag (any length >= N)"""
         def make():
             s = base._tables_host()[0]
             return C.upload(_pad(shift2(s), base.N + 8))
-        return self.get((id(base), base.N, base.id, "Se"), make)
+        return self.get((base.N, base.id, "Se"), make)
 
     def stencil_t(self, base, lg):
         """taps of S^T u: y_i = u_i + s_i u_{i+2}"""
-        return self.get((id(base), base.N, base.id, "ST", lg), lambda: unit_table(base._tables_host()[0], lg))
+        return self.get((base.N, base.id, "ST", lg), lambda: unit_table(base._tables_host()[0], lg))
 
     def tdma(self, base, lg):
         """(T0, T1) of the forward sweep g_i = (rhs_i - a_{i-2} g_{i-2}) / den_i and T1 of the back substitution
@@ -159,7 +159,7 @@ class TableCache:
             rden = 1.0 / den
             t1 = shift2(a, den.size) * rden
             return seg_table(rden, lg), seg_table(t1, lg), seg_table(w[: max(den.size - 2, 0)], lg)
-        return self.get((id(base), base.N, base.id, "tdma", lg), make)
+        return self.get((base.N, base.id, "tdma", lg), make)
 
     def fdma(self, plan, lg):
         """Plan_fdma (after FDMA_LU): forward x_i -= l_{i-2} x_{i-2}; backward x_i = (x_i - u1_i x_{i+2} -
@@ -169,13 +169,15 @@ class TableCache:
             rd = 1.0 / plan.d
             return (seg_table(shift2(plan.l, n), lg), seg_table(rd, lg), seg_table(_pad(plan.u1, n) * rd, lg),
                     seg_table(_pad(plan.u2, n) * rd, lg))
+        self._keep.append(plan)             # id() keys must not be recycled
         return self.get((id(plan), "fdma", lg), make)
 
     def band(self, band, lg):
         """unit tables of the diagonals of a Band (even offsets)"""
         def make():
             return [unit_table(band.host[d], lg) for d in range(band.ndiag)]
-        return self.get((id(band), "band", lg), make)
+        # keyed by content: the B matrices depend on the grid only (ensemble members share them)
+        return self.get((band.n_out, band.n_in, tuple(band.offsets), hash(band.host.tobytes()), "band", lg), make)
 
 
 # ------------------------------------------------------------------ programs

@@ -195,15 +195,19 @@ def test_slab_stepper_two_gpus():
     assert "SLAB OK" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
 
 
-def test_ensemble_members_match_standalone_runs():
-    """Ensemble (independent members on several streams, one CUDA graph each) == standalone runs."""
+@pytest.mark.parametrize("batched", [True, False])
+def test_ensemble_members_match_standalone_runs(batched):
+    """Ensemble == standalone runs.  batched: one launch list / one CUDA graph for all members (every pass takes a
+    job per member, dense DCT / projections / products through the batched entry points); not batched: one CUDA
+    graph per member on several streams."""
     import torch
     from pypde_b200.navier.ensemble import Ensemble
     from pypde_b200.navier import rbc2d
     kw = dict(case="rbc", shape=(32, 32), pr=1.0, dt=0.01, tsave=None, dealias=True, integrator="rk3",
               beta=1.0, aspect=1.0)
     ras = [1e4, 3e4, 1e5, 3e5, 1e6]
-    ens = Ensemble(ras, streams=3, **kw)
+    ens = Ensemble(ras, streams=3, batched=batched, **kw)
+    assert ens.batched == batched
     solo = [rbc2d.NavierStokes(ra=r, **kw) for r in ras]
     for m in ens.members + solo:
         m.set_velocity(m=1, n=1, amplitude=0.2)
@@ -214,9 +218,38 @@ def test_ensemble_members_match_standalone_runs():
             s.update()
     torch.cuda.synchronize()
     for m, s in zip(ens.members, solo):
-        assert torch.equal(m.T.vhat, s.T.vhat) and torch.equal(m.U.vhat, s.U.vhat)
+        for a, b in ((m.T.vhat, s.T.vhat), (m.U.vhat, s.U.vhat), (m.V.vhat, s.V.vhat), (m.pres.vhat, s.pres.vhat)):
+            assert rel_l2(H(a), H(b)) < 1e-13, rel_l2(H(a), H(b))
+        if not batched:
+            assert torch.equal(m.T.vhat, s.T.vhat) and torch.equal(m.U.vhat, s.U.vhat)
     # sharding: rank r of 2 gets every second member
     assert Ensemble(ras, rank=1, world=2, **kw).indices == [1, 3]
+
+
+def test_batched_ensemble_vs_oracle_128():
+    """configs[4] grid: 6 members of the 128 x 128 Ra sweep advanced together, two of them against the oracle."""
+    import torch
+    from pypde_b200.navier.ensemble import Ensemble
+    kw = dict(case="rbc", shape=(128, 128), pr=1.0, dt=0.005, tsave=None, dealias=True, integrator="rk3",
+              beta=1.0, aspect=1.0)
+    ras = list(np.logspace(4, 8, 6))
+    ens = Ensemble(ras, **kw)
+    assert ens.batched
+    for m in ens.members:
+        m.set_velocity(m=1, n=1, amplitude=0.2)
+        m.set_temperature(amplitude=0.2)
+    for _ in range(3):
+        ens.update()
+    torch.cuda.synchronize()
+    from oracle import pypde_port as P
+    for k in (0, 4):
+        o = P.RBC2D(ra=float(ras[k]), **kw)
+        o.set_velocity(m=1, n=1, amplitude=0.2)
+        o.set_temperature(amplitude=0.2)
+        o.iterate(3)
+        m = ens.members[k]
+        for t, r in ((m.T.vhat, o.That_), (m.U.vhat, o.Uhat), (m.V.vhat, o.Vhat), (m.pres.vhat, o.pres)):
+            assert rel_l2(H(t), r) < TOL, (k, rel_l2(H(t), r))
 
 
 def _preiterated_pair(cfg, pre):
