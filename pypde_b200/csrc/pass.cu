@@ -42,7 +42,9 @@ namespace pde {
 
 constexpr int PASS_MAX_INS = 16;             // instructions per program held in shared memory
 constexpr int PASS_SLOTS = 4;                // shared-memory table slots
-constexpr int PASS_MAX_JOBS_CACHED = 128;    // job descriptors held in shared memory
+// job descriptors held in shared memory: short sequences (ensembles of small grids) come as thousands of jobs and leave
+// most of the shared memory free
+__host__ __device__ constexpr int pass_jobs_cached(int lg) { return lg <= 3 ? 4096 : 128; }
 
 __device__ __forceinline__ void pcp16(void *smem, const void *gmem, int src_bytes)
 {
@@ -770,8 +772,10 @@ __device__ __forceinline__ void op_rec2(const Ctx &c, const pde_pass_ins &I)
     __syncwarp();
 }
 
+// Short sequences are latency-bound per strip (a handful of dependent memory round trips, little arithmetic): two
+// CTAs per SM (128 registers) instead of one (prof of the 256-member 128^2 ensemble: 25 us per strip with one).
 template <bool COL, int LG>
-__global__ void __launch_bounds__(LG <= 5 ? 256 : 64) k_pass(const pde_pass_job *__restrict__ jobs, int njobs)
+__global__ void __launch_bounds__(LG <= 5 ? 256 : 64, LG <= 3 ? 2 : 1) k_pass(const pde_pass_job *__restrict__ jobs, int njobs, int ncache)
 {
     extern __shared__ __align__(16) double2 pass_smem[];
     using Ctx = PassCtxT<LG, (LG <= 5 ? 8 : 2)>;
@@ -787,7 +791,6 @@ __global__ void __launch_bounds__(LG <= 5 ? 256 : 64) k_pass(const pde_pass_job 
     // job descriptors: one copy per CTA in shared memory (re-reading them from global memory cost ~10 % of the
     // first persistent version: four dependent L2 round trips per strip)
     pde_pass_job *sjobs = reinterpret_cast<pde_pass_job *>(sprog + PASS_MAX_INS);
-    const int ncache = njobs < PASS_MAX_JOBS_CACHED ? njobs : PASS_MAX_JOBS_CACHED;
     for (int t = threadIdx.x; t < ncache * (int)(sizeof(pde_pass_job) / 8); t += blockDim.x)
         reinterpret_cast<long long *>(sjobs)[t] = reinterpret_cast<const long long *>(jobs)[t];
     __syncthreads();
@@ -917,32 +920,35 @@ __global__ void k_peer_barrier(unsigned long long *const *__restrict__ peer_flag
 
 static int pass_width_for(int lg) { return lg <= 5 ? 8 : 2; }
 
-static size_t pass_smem_bytes(int lg)
+static int pass_ncache(int lg, int njobs) { return njobs < pass_jobs_cached(lg) ? njobs : pass_jobs_cached(lg); }
+
+static size_t pass_smem_bytes(int lg, int njobs)
 {
     const int W = pass_width_for(lg);
     const size_t nup = (size_t)32 << lg, bufu = nup + (lg > 0 ? 32 : 0) + 2;
     return (W * bufu + PASS_SLOTS * nup) * sizeof(double2) + PASS_MAX_INS * sizeof(pde_pass_ins) +
-           PASS_MAX_JOBS_CACHED * sizeof(pde_pass_job);
+           (size_t)pass_ncache(lg, njobs) * sizeof(pde_pass_job);
 }
 
 template <bool COL, int LG>
 static int launch_pass(int njobs, int max_nseq, const pde_pass_job *dev_jobs, cudaStream_t st)
 {
     constexpr int W = LG <= 5 ? 8 : 2;
-    const size_t smem = pass_smem_bytes(LG);
-    static PerDeviceFlag attr;
-    if (smem > 48 * 1024 && !attr.get()) {
+    const size_t smem = pass_smem_bytes(LG, njobs);
+    static PerDeviceSize attr;
+    if (smem > 48 * 1024 && smem > attr.get()) {
         PDE_CUDA(cudaFuncSetAttribute(k_pass<COL, LG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr.get() = true;
+        attr.get() = smem;
     }
     // persistent CTAs: as many as are resident at once, never more than there are strips
     int per_sm = (int)((227 * 1024) / (smem + 1024));
     per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
     while (per_sm > 1 && per_sm * 32 * W > 2048) --per_sm;
+    if (per_sm > (LG <= 3 ? 2 : 1)) per_sm = LG <= 3 ? 2 : 1;        // register budget of the kernel (__launch_bounds__)
     long strips = (long)njobs * ceil_div(max_nseq, W);
     long grid = (long)sm_count() * per_sm;
     if (grid > strips) grid = strips;
-    k_pass<COL, LG><<<(unsigned)grid, 32 * W, smem, st>>>(dev_jobs, njobs);
+    k_pass<COL, LG><<<(unsigned)grid, 32 * W, smem, st>>>(dev_jobs, njobs, pass_ncache(LG, njobs));
     return after_launch("pde_pass_run");
 }
 
