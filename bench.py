@@ -2,7 +2,7 @@
 """
 bench.py - headline benchmark of pypde_b200 (contract: see README / DESIGN.md §measurement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload rbc2048|rbc512|rbc64|ens128|diff1024]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload rbc2048|rbc512|rbc64|ens128|diff1024|dct]
     python bench.py --impl reference ...      # the reference's CPU path (oracle port) on the host cores
 
 Metric (BASELINE.json): RBC2D fp64 timesteps/sec at N x N.  A "step" is one full IMEX RK3 time
@@ -689,13 +689,111 @@ def run_diffusion(args):
     print(json.dumps(line))
 
 
+def run_dct(args):
+    """--workload dct (BASELINE.json configs[1]): batched Chebyshev forward / backward transforms
+    Base(N, "CH").forward_fft / backward_fft on (N, batch) arrays, N = 64 ... 4096 (and the FFT-friendly dealias
+    lengths 769 / 3073 the time step uses), both axes; GB/s = 8 (n_in + n_out) batch / t = 16 N batch / t.
+    value = median over the sweep.  A "step" is one pass over the whole sweep.  Single GPU."""
+    import torch
+    from pypde_b200 import Base, _cabi
+    from oracle import pypde_port as P
+    torch.cuda.set_device(0)
+    peaks, peak_src = measured_peaks()
+    sizes = (64, 128, 256, 512, 769, 1024, 2048, 3073, 4096)
+    algo_name = {1: "dense DMMA matrix", 2: "shared-memory FFT", 3: "Bluestein"}
+    cases = []
+    for N in sizes:
+        b = Base(N, "CH")
+        batch = max(1000, min(1_000_000, (1 << 27) // N))       # ~1 GB per array: larger than L2
+        x = torch.randn((N, batch), dtype=torch.float64, device="cuda")
+        xt = x.T.contiguous()
+        for name, fn, arr, axis in (("fwd0", b.forward_fft, x, 0), ("bwd0", b.backward_fft, x, 0),
+                                    ("fwd1", b.forward_fft, xt, 1), ("bwd1", b.backward_fft, xt, 1)):
+            cases.append((N, batch, b.plan.algo, name, fn, arr, axis))
+    sampler = ClockSampler(0)
+    for _ in range(args.warmup):
+        for N, batch, algo, name, fn, arr, axis in cases:
+            fn(arr, axis=axis)
+    torch.cuda.synchronize()
+    sampler.start()
+    _cabi.launch_count_reset()
+    times = {}
+    t_all0, t_all1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_all0.record()
+    evs = []
+    for _ in range(args.steps):
+        for k, (N, batch, algo, name, fn, arr, axis) in enumerate(cases):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn(arr, axis=axis)
+            e1.record()
+            evs.append((k, e0, e1))
+    t_all1.record()
+    torch.cuda.synchronize()
+    launches = _cabi.launch_count()
+    clocks = sampler.stop()
+    for k, e0, e1 in evs:
+        times.setdefault(k, []).append(e0.elapsed_time(e1))
+    sweep, gbs = [], []
+    for k, (N, batch, algo, name, fn, arr, axis) in enumerate(cases):
+        ms = float(np.median(times[k]))
+        g = 16.0 * N * batch / ms / 1e6
+        gbs.append(g)
+        sweep.append({"N": N, "batch": batch, "algo": algo_name.get(algo, str(algo)), "case": name, "ms": round(ms, 4),
+                      "GBps": round(g, 1), "frac_hbm": round(g / peaks["hbm_gbs"], 3)})
+    ms_total = t_all0.elapsed_time(t_all1)
+    # end to end on one size: host array in, host coefficients out
+    N, batch = 1024, 65536
+    b = Base(N, "CH")
+    hin = torch.randn((N, batch), dtype=torch.float64).pin_memory()
+    hout = torch.empty((N, batch), dtype=torch.float64).pin_memory()
+    dev = torch.empty((N, batch), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        dev.copy_(hin, non_blocking=True)
+        y = b.forward_fft(dev, axis=0)
+        hout.copy_(y, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    e2e_gbs = 3 * 16.0 * N * batch / e0.elapsed_time(e1) / 1e6
+    cpu = None
+    if not args.no_cpu_baseline:
+        o = P.Basis(2048, "CH")
+        xc = np.random.default_rng(0).standard_normal((2048, 2000))
+        o.forward(xc[:, :50])
+        t0 = time.perf_counter()
+        o.forward(xc)
+        tc = time.perf_counter() - t0
+        cpu = {"value": 16.0 * 2048 * 2000 / tc / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+               "sample": "scipy pocketfft dctn(type=1) + scaling of the oracle Basis(2048).forward on 2000 columns (%.2f s)" % tc}
+    best = max(sweep, key=lambda r: r["GBps"])
+    val = float(np.median(gbs))
+    line = {"metric": "dct1_fp64_GBps", "value": val, "unit": "GB/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "dct", "sizes": list(sizes), "cases": "forward / backward x axis 0 / axis 1", "value_is":
+                       "median GB/s over the sweep (16 bytes per element and transform)",
+                       "l2": "every array is ~1 GB (larger than the 126 MB L2)"},
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_gbs, "unit": "GB/s", "h2d_bytes_per_step": 8 * N * batch, "d2h_bytes_per_step": 8 * N * batch,
+                    "note": "Base(1024, CH).forward_fft on a pinned host (1024 x 65536) array, copies inside the timed region"},
+            "roofline": {"kernel": "batched DCT-I (best case of the sweep: N = %d %s, %s)" % (best["N"], best["case"], best["algo"]),
+                         "bound": "hbm", "achieved": best["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": best["GBps"] / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src},
+            "sweep": sweep, "cpu_baseline": cpu}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="rbc2048", choices=sorted(WORKLOADS) + ["ens128", "diff1024"])
+    ap.add_argument("--workload", default="rbc2048", choices=sorted(WORKLOADS) + ["ens128", "diff1024", "dct"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
@@ -704,6 +802,10 @@ def main():
         if args.impl == "reference":
             raise SystemExit("--impl reference times the rbc workloads; the ensemble's CPU number is its cpu_baseline")
         return run_ensemble(args)
+    if args.workload == "dct":
+        if args.impl == "reference":
+            raise SystemExit("--impl reference times the rbc workloads; the transform sweep's CPU number is its cpu_baseline")
+        return run_dct(args)
     if args.workload == "diff1024":
         if args.impl == "reference":
             raise SystemExit("--impl reference times the rbc workloads; diff1024's CPU number is its cpu_baseline")

@@ -227,7 +227,13 @@ class NavierStokes(NavierStokesBase, NavierStokesSteadyState, Integrator):
                 import torch.distributed as dist
                 from .pass_slab_stepper import PassSlabStepper
                 if self._stepper_kind == "fast" and PassSlabStepper.supported(self, dist.get_world_size()):
-                    self._fast = PassSlabStepper(self)   # peer-memory row passes, no NCCL on the data path
+                    # peer-memory row passes, no NCCL on the data path; "yfirst": the 8-exchange schedule
+                    import os
+                    if os.environ.get("PDE_SLAB_SCHEDULE", "yfirst") == "yfirst":
+                        from .pass_slab_stepper2 import PassSlabStepperY
+                        self._fast = PassSlabStepperY(self)
+                    else:
+                        self._fast = PassSlabStepper(self)
                 else:
                     from .slab_stepper import SlabStepper
                     self._fast = SlabStepper(self)       # NCCL all-to-all transposes ("batched")
