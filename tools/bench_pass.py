@@ -42,8 +42,11 @@ def main():
         "py4_like": lambda p, a, b, c: p.load(a).band(band).fdma(plan).store(b).stencil(base).store(c),
     }
     out = {"n": n, "njobs": njobs, "rows": []}
+    only = sys.argv[2] if len(sys.argv) > 2 else None
     for layout in (PS.ROW, PS.COL):
         for name, build in progs.items():
+            if only and name != only:
+                continue
             L = PS.PassLaunch(layout, n, PS.TableCache())
             for j in range(njobs):
                 build(L.job(n), A[j], B[j], C2[j])
