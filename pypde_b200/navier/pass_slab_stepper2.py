@@ -113,6 +113,21 @@ class PassSlabStepperY(PassSlabStepper):
             dst = PS.Operand([self.mem.base[s] + yo + 8 * c0], [ld], [0, w], w, keep=(self.mem,))
             L.job(nrows).load(srcarr[row0:row0 + nrows, :w]).store(dst)
 
+    def yseg(self, yname, parts, nrows_total):
+        """COL-layout operand: column q of my slab, rows split over their owners -- the Y-layout array `yname` of every
+        rank, at my column offset.  A column pass that stores through it writes 64-byte row pieces (8 columns) straight
+        into the peers' row slabs (PDE_SLAB_COLPUSH=1; the default is a local store + a row pass that pushes 2 KB pieces)."""
+        yo, _ = self.yoff[yname]
+        ld = self.yld[yname]
+        ptrs, starts = [], []
+        for s, (row0, nrows) in enumerate(parts):
+            if nrows <= 0:
+                continue
+            ptrs.append(self.mem.base[s] + yo + 8 * self.lay.c0)
+            starts.append(row0)
+        starts.append(nrows_total)
+        return PS.Operand(ptrs, [ld] * len(ptrs), starts, nrows_total, keep=(self.mem,))
+
     def push_y2x_wide(self, L, src, xname, nrows, row0):
         """rows of a local Y-layout array with D1 columns -> the X-layout arrays (column partition dcp) of all ranks;
         rows longer than 4096 elements' worth of one pass are cut at column 2048"""
@@ -175,18 +190,27 @@ class PassSlabStepperY(PassSlabStepper):
             calls.add(fn, *args, label="peer_barrier")
 
         # ---- PX1 (local): F -> Sx F, dx Sx F / sx; pres -> dpdx; pushed to the row owners
+        import os
+        colpush = os.environ.get("PDE_SLAB_COLPUSH", "0") == "1"
         L = PS.PassLaunch(PS.COL, N0, self.tables)
-        for k in names:
-            L.job(M1c).load(state[k]).stencil(xb[k]).store(xl("c" + k, N0, M1c)).diff(sx).store(xl("d" + k, N0, M1c))
-        L.job(W).load(pres).diff(sx).store(xl("dpdx", N0, W))
-        add(L)
-        L = PS.PassLaunch(PS.ROW, lay.Wmax, self.tables)
-        for k in names:
-            self.push_x2y(L, "c" + k, "y_c" + k, lay.rp, M1)
-            self.push_x2y(L, "d" + k, "y_d" + k, lay.rp, M1)
-        self.push_x2y(L, "pres", "y_pres", lay.rp, N1)
-        self.push_x2y(L, "dpdx", "y_dpdx", lay.rp, N1)
-        add(L, "exchange[push c, d, pres, dpdx]")
+        if colpush:
+            for k in names:
+                L.job(M1c).load(state[k]).stencil(xb[k]).store(self.yseg("y_c" + k, lay.rp, N0)).diff(sx) \
+                    .store(self.yseg("y_d" + k, lay.rp, N0))
+            L.job(W).load(pres).store(self.yseg("y_pres", lay.rp, N0)).diff(sx).store(self.yseg("y_dpdx", lay.rp, N0))
+            add(L)
+        else:
+            for k in names:
+                L.job(M1c).load(state[k]).stencil(xb[k]).store(xl("c" + k, N0, M1c)).diff(sx).store(xl("d" + k, N0, M1c))
+            L.job(W).load(pres).diff(sx).store(xl("dpdx", N0, W))
+            add(L)
+            L = PS.PassLaunch(PS.ROW, lay.Wmax, self.tables)
+            for k in names:
+                self.push_x2y(L, "c" + k, "y_c" + k, lay.rp, M1)
+                self.push_x2y(L, "d" + k, "y_d" + k, lay.rp, M1)
+            self.push_x2y(L, "pres", "y_pres", lay.rp, N1)
+            self.push_x2y(L, "dpdx", "y_dpdx", lay.rp, N1)
+            add(L, "exchange[push c, d, pres, dpdx]")
         barrier()
         # ---- PY2 (local rows): y stencils / derivatives, right-hand-side parts
         eU, eV, fU, fV, fT, gU, gV, gT = self.eY
@@ -244,14 +268,15 @@ class PassSlabStepperY(PassSlabStepper):
             p = L.job(M1c).load(xl("h" + k, N0, M1c)).band(solver[k].plan_for_rhs[0].band) \
                 .fdma(solver[k].plan_for_lhs[0]).store(state[k])
             if k == "U":
-                p.stencil(xb["U"]).diff(sx).store(xl("aUx", N0, M1c))
+                p.stencil(xb["U"]).diff(sx).store(self.yseg("y_aUx", lay.rp, N0) if colpush else xl("aUx", N0, M1c))
             elif k == "V":
-                p.stencil(xb["V"]).store(xl("aVx", N0, M1c))
+                p.stencil(xb["V"]).store(self.yseg("y_aVx", lay.rp, N0) if colpush else xl("aVx", N0, M1c))
         add(L)
-        L = PS.PassLaunch(PS.ROW, lay.Wmax, self.tables)
-        self.push_x2y(L, "aUx", "y_aUx", lay.rp, M1)
-        self.push_x2y(L, "aVx", "y_aVx", lay.rp, M1)
-        add(L, "exchange[push div parts]")
+        if not colpush:
+            L = PS.PassLaunch(PS.ROW, lay.Wmax, self.tables)
+            self.push_x2y(L, "aUx", "y_aUx", lay.rp, M1)
+            self.push_x2y(L, "aVx", "y_aVx", lay.rp, M1)
+            add(L, "exchange[push div parts]")
         barrier()
         # ---- PYd: div = Sy (dx Sx U / sx) + dz Sy (Sx V) / sz; R' = div Hy^T; both pushed
         sp = ns.solver_P
@@ -269,11 +294,13 @@ class PassSlabStepperY(PassSlabStepper):
         barrier()
         # ---- PX6 (local): q = Bx R'; per-column Poisson solves; pushed to the row owners
         L = PS.PassLaunch(PS.COL, N0, self.tables)
-        L.job(M1c).load(xl("R", N0, M1c)).band(sp.plan_for_rhs[0].band).poisson(self.ptab).store(xl("R", M0, M1c))
+        p = L.job(M1c).load(xl("R", N0, M1c)).band(sp.plan_for_rhs[0].band).poisson(self.ptab)
+        p.store(self.yseg("WY", mparts, M0) if colpush else xl("R", M0, M1c))
         add(L)
-        L = PS.PassLaunch(PS.ROW, lay.Wmax, self.tables)
-        self.push_x2y(L, "R", "WY", mparts, M1)
-        add(L, "exchange[push W]")
+        if not colpush:
+            L = PS.PassLaunch(PS.ROW, lay.Wmax, self.tables)
+            self.push_x2y(L, "R", "WY", mparts, M1)
+            add(L, "exchange[push W]")
         barrier()
         # ---- P = W Qy^T on my rows; PY7: P[0,0] = 0, e1 = Sy P, bU = Gy e1, bV = Gy dz e1 / sz (pushed)
         WY = yl("WY", M0r, M1)

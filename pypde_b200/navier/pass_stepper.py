@@ -125,8 +125,9 @@ class PassStepper(FastStepper):
 
     def _dct_members(self, calls, plan, mode, axis, pick_x, pick_y):
         """one axis of a 2-D transform for all members: pick_x / pick_y map a member to its list of arrays"""
-        if len(self.runs) == 1:
+        if len(self.runs) == 1 and plan.algo != 1:
             return self._dct(calls, plan, mode, axis, pick_x(self.mb[0]), pick_y(self.mb[0]))
+        # dense-matrix transforms (small grids): all arrays of all members in ONE batched GEMM launch
         xs = [x for m in self.mb for x in pick_x(m)]
         ys = [y for m in self.mb for y in pick_y(m)]
         x, y = xs[0], ys[0]
