@@ -240,3 +240,50 @@ def test_lincomb(axis, n, nseq):
     want2 = want.copy()
     want2 += 2.0 * hs[0] - hs[2]
     assert rel_l2(out2.cpu().numpy(), want2) < 1e-15
+
+
+def test_batched_gemm_dct_products():
+    """pde_gemm_f64_batched / pde_dct1_batched / pde_conv_products_members (one launch for many members) against
+    the per-array entry points and NumPy."""
+    import ctypes
+    torch, C, PS = _mods()
+    from pypde_b200 import ops
+    rng = np.random.default_rng(2)
+    nb, m, n, k = 7, 50, 38, 44
+    A = [torch.as_tensor(rng.standard_normal((m, k)), device="cuda") for _ in range(nb)]
+    B = torch.as_tensor(rng.standard_normal((n, k)), device="cuda")
+    Cs = [torch.zeros((m, n), dtype=torch.float64, device="cuda") for _ in range(nb)]
+    pa = torch.tensor([a.data_ptr() for a in A], dtype=torch.int64, device="cuda")
+    pc = torch.tensor([c.data_ptr() for c in Cs], dtype=torch.int64, device="cuda")
+    C.check(C.lib().pde_gemm_f64_batched(1, None, ctypes.c_void_p(pa.data_ptr()), k, C.p(B), None, k,
+                                         ctypes.c_void_p(pc.data_ptr()), n, m, n, k, nb, 1, C.stream()))
+    for a, c in zip(A, Cs):
+        assert rel_l2(c.cpu().numpy(), a.cpu().numpy() @ B.cpu().numpy().T) < 1e-14
+        assert torch.equal(c, ops.gemm(a, B, transB=True))
+    # dense DCT, both axes, truncated / padded
+    L = 97
+    plan = ops.DctPlan.get(L)
+    assert plan.algo == 1
+    for axis in (0, 1):
+        xs = [torch.as_tensor(rng.standard_normal((64, 30) if axis == 0 else (30, 64)), device="cuda") for _ in range(5)]
+        ys = [torch.zeros((L, 30) if axis == 0 else (30, L), dtype=torch.float64, device="cuda") for _ in range(5)]
+        px = torch.tensor([x.data_ptr() for x in xs], dtype=torch.int64, device="cuda")
+        py = torch.tensor([y.data_ptr() for y in ys], dtype=torch.int64, device="cuda")
+        C.check(C.lib().pde_dct1_batched(plan.handle, ops.BWD, 5, ctypes.c_void_p(px.data_ptr()), xs[0].stride(0), 64,
+                                         ctypes.c_void_p(py.data_ptr()), ys[0].stride(0), L, 30, axis, 1, C.stream()))
+        for x, y in zip(xs, ys):
+            assert torch.equal(y, ops.dct1(plan, ops.BWD, x, axis=axis, n_out=L))
+    # products of 3 members with a shared boundary term
+    nm, npts = 3, 1000
+    arrs = [torch.as_tensor(rng.standard_normal((nm, npts)), device="cuda") for _ in range(10)]
+    u, w, uo, wo, dxU, dzU, dxV, dzV, dxT, dzT = arrs
+    dTbc = torch.as_tensor(rng.standard_normal(npts), device="cuda")
+    ref = [t.clone() for t in (dxU, dxV, dxT)]
+    for mm in range(nm):
+        C.check(C.lib().pde_conv_products(npts, 0.4, -0.3, C.p(u[mm]), C.p(w[mm]), C.p(uo[mm]), C.p(wo[mm]), C.p(ref[0][mm]),
+                                          C.p(dzU[mm]), C.p(ref[1][mm]), C.p(dzV[mm]), C.p(ref[2][mm]), C.p(dzT[mm]),
+                                          C.p(dTbc), C.stream()))
+    C.check(C.lib().pde_conv_products_members(npts, nm, npts, 0.4, -0.3, C.p(u), C.p(w), C.p(uo), C.p(wo), C.p(dxU), C.p(dzU),
+                                              C.p(dxV), C.p(dzV), C.p(dxT), C.p(dzT), C.p(dTbc), C.stream()))
+    for a, b in zip((dxU, dxV, dxT), ref):
+        assert torch.equal(a, b)
