@@ -285,7 +285,8 @@ int pde_slab_repack(int dir, double *bundle, double *blocked, int rows, int K, i
  *   TABLES  stage n <= 4 recurrence tables p[k] (segment order, NUP double2 each) in the shared-memory slots
  *           k = 0..n-1; executed once per thread block and job
  *   LOAD    buffer <- operand[0..n), zero beyond
- *   STORE   operand[0..n) <- buffer           (flag ONLY_SEQ: only the sequence with global index off[0])
+ *   STORE   operand[0..n) <- buffer           (flag ONLY_SEQ: only the sequence with global index off[0];
+ *           flag BULK, ROW layout: cp.async.bulk shared -> global copies of 16 SEGU bytes, one per lane)
  *   AXPY    buffer <- buffer + f0 operand[0..n)   (flag SCALED: f1 buffer + f0 operand;
  *           flag STENCIL: the image operand_i + st_i operand_{i-2}, i < n + 2, of the n operand entries,
  *           with the element table st = p[7])
@@ -324,6 +325,7 @@ int pde_slab_repack(int dir, double *bundle, double *blocked, int rows, int K, i
 #define PDE_PASS_F_STENCIL 8
 #define PDE_PASS_F_ONLY_SEQ 16
 #define PDE_PASS_F_ACCUM 32
+#define PDE_PASS_F_BULK 64      /* ROW STORE: hand the row's 32 segments to the TMA bulk-copy engine (cp.async.bulk) */
 typedef struct {
     int op;
     int n;

@@ -248,6 +248,38 @@ __device__ __forceinline__ void op_store(const Ctx &c, const pde_pass_ins &I)
     const bool one = I.nseg == 1;
     if (!COL) {
         if (!c.live || (only && c.seq0 + c.q != I.off[0])) return;
+        if ((I.flags & PDE_PASS_F_BULK) && Ctx::SEGU >= 8) {
+            // TMA bulk stores: lane l hands its segment (SEGU units = 16 SEGU contiguous bytes of the row) to the copy
+            // engine, cut at the operand's segment boundaries (peer slabs); shared-memory writes of the generic proxy
+            // are fenced first, and the buffer is reused only after the engine has read it.
+            __syncwarp();
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            const int e0 = 2 * c.lane * Ctx::SEGU;
+            const int e1 = min(n, e0 + 2 * Ctx::SEGU);
+            const double2 *sseg = c.buf + c.segbase();
+            if (e1 > e0) {
+                const int efull = e0 + ((e1 - e0) & ~1);
+                int a = e0;
+                while (a < efull) {
+                    const int s = seg_of(I, a);
+                    const int send = (s + 1 < I.nseg) ? I.start[s + 1] : n;
+                    const int b = min(efull, send);
+                    const double *g = elem_addr<false>(I, s, c.q, a);
+                    const unsigned sa = (unsigned)__cvta_generic_to_shared(sseg + ((a - e0) >> 1));
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(g), "r"(sa), "r"((b - a) * 8)
+                                 : "memory");
+                    a = b;
+                }
+                if (efull < e1) {       // odd tail element
+                    const int s = seg_of(I, efull);
+                    *const_cast<double *>(elem_addr<false>(I, s, c.q, efull)) = sseg[(efull - e0) >> 1].x;
+                }
+            }
+            asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+            __syncwarp();
+            return;
+        }
         double *row0 = const_cast<double *>(reinterpret_cast<const double *>(I.p[0])) + (long)c.q * I.ld[0] + 2 * c.lane;
         const double2 *src = c.buf + RowMap<Ctx>::base(c.lane);
         const int rem0 = n - 2 * c.lane;

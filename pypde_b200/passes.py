@@ -28,7 +28,9 @@ MAX_INS = 16
 SLOTS = 4
 COL, ROW = 0, 1
 LOAD, STORE, AXPY, SCALE, SETZ0, POINT, DIFF, REC1, REC2, TABLES, LINCOMB = 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11
-F_DESC, F_PERSEQ, F_SCALED, F_STENCIL, F_ONLY_SEQ, F_ACCUM = 1, 2, 4, 8, 16, 32
+F_DESC, F_PERSEQ, F_SCALED, F_STENCIL, F_ONLY_SEQ, F_ACCUM, F_BULK = 1, 2, 4, 8, 16, 32, 64
+import os as _os
+BULK_STORES = _os.environ.get("PDE_PASS_BULK", "1") == "1"      # ROW stores through the TMA bulk-copy engine
 
 
 class PassIns(ctypes.Structure):
@@ -242,6 +244,8 @@ class Program:
     def store(self, x, only_seq=None):
         i = self._new(STORE)
         self._opnd(x).fill(i)
+        if BULK_STORES and self.L.layout == ROW and only_seq is None:
+            i.flags |= F_BULK
         if only_seq is not None:
             i.flags |= F_ONLY_SEQ
             i.off[0] = int(only_seq)
