@@ -21,6 +21,8 @@
 #include "common.cuh"
 #include <cmath>
 #include <vector>
+#include <algorithm>
+#include <cstdlib>
 
 namespace pde {
 
@@ -454,6 +456,10 @@ int fft_dct_exec(FftDctPlan *p, int mode, int njobs, const double *const *xs, lo
             return PDE_ERR_UNSUPPORTED;
         }
         return rc;
+    }
+    if (axis == 1) {   // contiguous rows, 16-byte aligned: persistent CTAs with TMA-prefetched rows
+        const int rc = dispatch_row_tma(p, mode, njobs, ptrs, ldx, n_in, ldy, n_out, batch, st);
+        if (rc >= 0) return rc;
     }
     {   // compile-time specialised kernels for the hot lengths
         const int rc = axis == 1 ? dispatch_fft_t<1>(p, mode, njobs, ptrs, ldx, n_in, ldy, n_out, batch, st)

@@ -12,6 +12,12 @@
 
 namespace pde {
 
+__device__ __forceinline__ void cp_async8_fft(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem)
+                 : "memory");
+}
+
 template <>
 __device__ __forceinline__ void dft<8>(double2 *a)
 {
@@ -134,6 +140,34 @@ struct SeqPad {
 // x1.33 / x2 on passes 2 / 3 of P = 3072, x8 on the radix-8 pass of P = 2048).  Instead consecutive
 // butterflies walk the FIRST-LEVEL blocks (pitch M1 + 1 elements, odd, so 8 lanes hit 8 bank groups), then
 // the blocks inside a first-level block, and j is the slowest index (its twiddles become warp broadcasts).
+// Twiddle multiplication a_r *= w^r of one butterfly; ld(r) loads w^r from the pass table.  -DPDE_FFT_TWPOW: a radix-16
+// butterfly loads only w^1, w^2, w^3, w^4, w^8, w^12 and forms the other nine as products w^{4q} w^b (9 complex
+// multiplications instead of 9 16-byte L1 requests per thread: the kernels are L1TEX-bound, the fp64 pipe is 30 % busy).
+// The products carry one more rounding (<= 1.5 ulp instead of 0.5 ulp per twiddle).
+template <int R, class LD>
+__device__ __forceinline__ void twiddle_mul(double2 *a, LD ld)
+{
+#ifdef PDE_FFT_TWPOW
+    if constexpr (R == 16) {
+        const double2 w1 = ld(1), w2 = ld(2), w3 = ld(3);
+        a[1] = cmul(a[1], w1);
+        a[2] = cmul(a[2], w2);
+        a[3] = cmul(a[3], w3);
+#pragma unroll
+        for (int q = 1; q < 4; ++q) {
+            const double2 wq = ld(4 * q);
+            a[4 * q] = cmul(a[4 * q], wq);
+            a[4 * q + 1] = cmul(a[4 * q + 1], cmul(wq, w1));
+            a[4 * q + 2] = cmul(a[4 * q + 2], cmul(wq, w2));
+            a[4 * q + 3] = cmul(a[4 * q + 3], cmul(wq, w3));
+        }
+        return;
+    }
+#endif
+#pragma unroll
+    for (int r = 1; r < R; ++r) a[r] = cmul(a[r], ld(r));
+}
+
 template <int WOFF, int P, int M1, int NCUR, int S, int T, int R, int SP = 0>
 __device__ __forceinline__ void dif_pass_t(double2 *z, const double2 *__restrict__ W)
 {
@@ -193,11 +227,8 @@ __device__ __forceinline__ void dif_pass_t(double2 *z, const double2 *__restrict
 #pragma unroll
         for (int r = 0; r < R; ++r) a[r] = p[r * RS];
         dft<R>(a);
-        if (M > 1) {
-#pragma unroll
-            for (int r = 1; r < R; ++r)
-                a[r] = cmul(a[r], WOFF < 0 ? __ldg(W + j * (r * TWS)) : __ldg(W + WOFF + (r - 1) * M + j));
-        }
+        if (M > 1)
+            twiddle_mul<R>(a, [&](int r) { return WOFF < 0 ? __ldg(W + j * (r * TWS)) : __ldg(W + WOFF + (r - 1) * M + j); });
 #pragma unroll
         for (int r = 0; r < R; ++r) p[r * RS] = a[r];
     }
@@ -493,6 +524,202 @@ k_dct_fft_t(const double2 *__restrict__ W, const double2 *__restrict__ CS, int m
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Axis 1 (contiguous rows), one sequence per CTA pass, PERSISTENT CTAs with a TMA-prefetched input row.
+//
+// ncu on k_dct_fft_t<3072, 1, 192, 1, ...> (profiles/r02_ncu_stage.csv): L1TEX 83 % busy, ~5500 wavefronts per
+// sequence -- 3400 shared-memory wavefronts of the four z sweeps, the rest global loads (input row, twiddles) that
+// share the same pipe -- and 4.4 long-scoreboard stalls per issue: every CTA waits for its own row before it can
+// start.  Here a CTA loops over rows; while it runs passes 2.. and the split of row i, the copy engine
+// (cp.async.bulk.shared::cluster.global + mbarrier complete_tx: no LSU wavefronts, no registers) brings row i+1 into
+// a 24 KB staging buffer.  The first radix-16 pass reads its 16 inputs straight from that buffer (real data: half the
+// bytes of the packed z, and the zero-padded part of a backward transform is never read), so the load phase's
+// z store and the first pass's z load disappear: 6.5 instead of 8 shared sweeps, no exposed global latency.
+// Needs 16-byte aligned rows (even ldx); 49.4 + 24.6 KB of shared memory per CTA = 3 CTAs per SM as before.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@p bra DONE_%=;\n"
+                 "bra WAIT_%=;\n"
+                 "DONE_%=:\n"
+                 "}\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_load(void *smem, const void *gmem, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem)),
+                 "l"(gmem), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+
+template <int P, int T, int... RAD>
+__global__ void __maxnreg__((FftRegs<P, 1, T, 16>::value))
+k_dct_row_tma(const double2 *__restrict__ W, const double2 *__restrict__ CS, int mode, const __grid_constant__ DctPtrs ptrs,
+              long ldx, int n_in,
+              long ldy, int n_out, int batch, int nitems)
+{
+    static_assert(FirstRadix<RAD...>::value == 16 && T == P / 16, "one radix-16 first-pass butterfly per thread");
+    extern __shared__ __align__(128) double2 zsm[];
+    constexpr int R = 16, M = P / R, H = P / 2;
+    using PD = Pad<P, M, 0>;
+    constexpr int PS = PD::SEQ, RAWN = P + 2;
+    double *raw = reinterpret_cast<double *>(zsm + PS);
+    unsigned long long *bar = reinterpret_cast<unsigned long long *>(raw + RAWN);
+    const bool bwd = mode == PDE_DCT_BWD, fwd = mode == PDE_DCT_FWD;
+    const double se = bwd ? 0.5 : 1.0, so = bwd ? -0.5 : 1.0;
+    const int j = threadIdx.x;
+    const unsigned even_bytes = (unsigned)(n_in & ~1) * 8u;
+
+    auto issue = [&](int item) {              // thread 0: start the copy of one row
+        const int job = item / batch, q = item - job * batch;
+        const double *src = ptrs.x[job] + (long)q * ldx;
+        mbar_expect_tx(bar, even_bytes);
+        if (even_bytes) bulk_load(raw, src, even_bytes, bar);
+        if (n_in & 1) {                        // odd tail element: the bulk copy moves multiples of 16 bytes
+            cp_async8_fft(raw + n_in - 1, src + n_in - 1);
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+    if (j == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        if ((int)blockIdx.x < nitems) issue(blockIdx.x);
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+    }
+    __syncthreads();
+
+    unsigned phase = 0;
+    for (int item = blockIdx.x; item < nitems; item += gridDim.x, phase ^= 1u) {
+        const int job = item / batch, q = item - job * batch;
+        double *__restrict__ yrow = ptrs.y[job] + (long)q * ldy;
+        mbar_wait(bar, phase);
+        // ---- first pass: z_m = (e_2m, e_2m+1), m = j + r M; m < H: (x_2m, x_2m+1); m >= H: (x_{2P-2m}, x_{2P-2m-1})
+        double2 a[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int m = j + r * M;
+            double v0, v1;
+            if (r < R / 2) {
+                const int n0 = 2 * m;
+                if (n0 + 1 < n_in) {
+                    const double2 t = *reinterpret_cast<const double2 *>(raw + n0);
+                    v0 = t.x;
+                    v1 = t.y;
+                } else {
+                    v0 = n0 < n_in ? raw[n0] : 0.0;
+                    v1 = 0.0;
+                }
+            } else {
+                const int n0 = 2 * P - 2 * m;
+                v0 = n0 < n_in ? raw[n0] : 0.0;
+                v1 = n0 - 1 < n_in ? raw[n0 - 1] : 0.0;
+            }
+            const bool edge = (r == 0 || r == R / 2) && j == 0;        // x_0 and x_P are not scaled
+            a[r] = make_double2(v0 * (edge ? 1.0 : se), v1 * so);
+        }
+        dft<R>(a);
+        twiddle_mul<R>(a, [&](int r) { return __ldg(W + (r - 1) * M + j); });
+        {
+            double2 *p = zsm + j;
+#pragma unroll
+            for (int r = 0; r < R; ++r) p[r * (M + 1)] = a[r];
+        }
+        __syncthreads();                       // z complete; the staging buffer is free
+        const int next = item + gridDim.x;
+        if (j == 0 && next < nitems) issue(next);
+        TailPasses<RAD...>::template run<0, P, M, 1, T>(zsm, W);
+        // ---- split + store: y_k = (A_k + conj(A_{P-k}))/2 - i e^{-i pi k / P} (A_k - conj(A_{P-k}))/2
+        const double fs = 1.0 / (2.0 * (double)P);
+        auto split_one = [&](int k) {
+            const int k2 = P - k;
+            const int kk = k == 0 ? 0 : k2;
+            const double2 av = zsm[DigitRev<P, RAD...>::pos(k) + k % R];
+            const double2 bv = zsm[DigitRev<P, RAD...>::pos(kk) + kk % R];
+            const double2 cs = __ldg(CS + k);
+            const double sr = av.x + bv.x, dr = av.x - bv.x, si = av.y + bv.y;
+            const double h = fwd ? (k == 0 ? 0.5 * fs : ((k & 1) ? -fs : fs)) : 0.5;
+            const double t = cs.x * si - cs.y * dr;
+            if (k < n_out) yrow[k] = h * (sr + t);
+            if (k2 != k && k2 < n_out) yrow[k2] = h * (sr - t);
+        };
+        static_assert(H % T == 0, "split mapping");
+#pragma unroll
+        for (int it = 0; it < H / T; ++it) split_one(it * T + j);
+        if (j == 0) {
+            split_one(H);
+            asm volatile("cp.async.wait_all;\n" ::: "memory");      // tail element of the next row (issued long ago)
+        }
+        __syncthreads();                       // z free for the next row
+    }
+}
+
+template <int P, int T, int... RAD>
+static int launch_row_tma(const FftDctPlan *p, int mode, int njobs, const DctPtrs &ptrs, long ldx, int n_in, long ldy,
+                          int n_out, int batch, cudaStream_t st)
+{
+    auto kern = k_dct_row_tma<P, T, RAD...>;
+    constexpr int M1 = P / 16;
+    constexpr size_t smem = (size_t)Pad<P, M1, 0>::SEQ * 16 + (size_t)(P + 2) * 8 + 16;
+    if (!p->Wp) {
+        std::vector<double2> tab;
+        build_pass_tables<RAD...>(P, P, tab);
+        double2 *d = nullptr;
+        PDE_CUDA(cudaMalloc(&d, sizeof(double2) * tab.size()));
+        PDE_CUDA(cudaMemcpy(d, tab.data(), sizeof(double2) * tab.size(), cudaMemcpyHostToDevice));
+        const_cast<FftDctPlan *>(p)->Wp = d;
+    }
+    constexpr int per_cta = (int)smem + 1024;
+    constexpr int fit = 227 * 1024 / per_cta;
+    constexpr int ctas = fit < 3 ? (fit < 1 ? 1 : fit) : 3;
+    static PerDeviceFlag attr;
+    if (!attr.get()) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, per_cta * ctas * 100 / (228 * 1024) + 1);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(k_dct_row_tma): %s", cudaGetErrorString(e));
+            return PDE_ERR_CUDA;
+        }
+        attr.get() = true;
+    }
+    const long nitems = (long)njobs * batch;
+    const int grid = (int)std::min<long>(nitems, (long)ctas * sm_count());
+    kern<<<grid, T, smem, st>>>(p->Wp, p->CS, mode, ptrs, ldx, n_in, ldy, n_out, batch, (int)nitems);
+    return after_launch("pde_dct1(fft, persistent rows)");
+}
+
+// rows through the persistent TMA kernel: 16-byte aligned rows, a specialised length; PDE_DCT_TMA=0 disables
+static int dispatch_row_tma(const FftDctPlan *p, int mode, int njobs, const DctPtrs &ptrs, long ldx, int n_in, long ldy,
+                            int n_out, int batch, cudaStream_t st)
+{
+    static const bool enabled = !(getenv("PDE_DCT_TMA") && atoi(getenv("PDE_DCT_TMA")) == 0);
+    if (!enabled || (ldx & 1) || n_in > p->P + 1) return -1;
+    for (int jn = 0; jn < njobs; ++jn)
+        if ((unsigned long long)ptrs.x[jn] & 15) return -1;
+    switch (p->P) {
+    case 3072: return launch_row_tma<3072, 192, 16, 16, 12>(p, mode, njobs, ptrs, ldx, n_in, ldy, n_out, batch, st);
+    case 2048: return launch_row_tma<2048, 128, 16, 16, 8>(p, mode, njobs, ptrs, ldx, n_in, ldy, n_out, batch, st);
+    case 4096: return launch_row_tma<4096, 256, 16, 16, 16>(p, mode, njobs, ptrs, ldx, n_in, ldy, n_out, batch, st);
+    default: return -1;
+    }
+}
+
 template <int P, int S, int T, int AXIS, int... RAD>
 static int launch_fft_t(const FftDctPlan *p, int mode, int njobs, const DctPtrs &ptrs, long ldx, int n_in, long ldy,
                         int n_out, int batch, cudaStream_t st)
@@ -548,6 +775,10 @@ static int dispatch_fft_t(const FftDctPlan *p, int mode, int njobs, const DctPtr
     // selects the radix-4 + radix-3 tail for comparison
     static const bool radix12 = !(getenv("PDE_FFT_RADIX12") && atoi(getenv("PDE_FFT_RADIX12")) == 0);
     if (radix12) {
+        // PDE_FFT_AXIS0_S=2: two columns per CTA (99 KB, 2 CTAs per SM, 16-byte row pieces) instead of four (197 KB, 1 CTA)
+        static const int s0 = getenv("PDE_FFT_AXIS0_S") ? atoi(getenv("PDE_FFT_AXIS0_S")) : 4;
+        if (AXIS == 0 && s0 == 2 && p->P == 3072)
+            return launch_fft_t<3072, 2, 192, AXIS, 16, 16, 12>(p, mode, njobs, ptrs, ldx, n_in, ldy, n_out, batch, st);
         if (AXIS == 0) {
             switch (p->P) {
                 PDE_FFT_CASE(1536, 4, 384, 16, 8, 12)

@@ -144,36 +144,10 @@ static_assert(true, "");
 
 constexpr int PB = 8;        // independent memory operations per batch
 
-// COL layout, 16-byte form: thread (rq, cp) owns the 2 x 2 blocks (rows 2u, 2u+1) x (columns 2cp, 2cp+1), u = rq + 64 j:
-// one 16-byte global access per row (two adjacent columns) and one 16-byte shared access per column (two consecutive
-// rows = one unit) -- half the memory instructions of the 8-byte form.  Needs 16-byte aligned rows (even leading
-// dimension); the 8-byte form stays as the fallback (segments, odd pitches, stencil-on-load, single-sequence stores).
-template <class Ctx>
-struct Col16 {
-    static constexpr int LG = Ctx::lg, HP = Ctx::W / 2;
-    static constexpr int STEPS = (Ctx::NUP + 63) / 64;
-    int cp, rq;
-    __device__ __forceinline__ Col16() : cp(threadIdx.x % (HP > 0 ? HP : 1)), rq(threadIdx.x / (HP > 0 ? HP : 1)) {}
-    __device__ __forceinline__ int ubase() const { return rq + (Ctx::PADU ? (rq >> LG) : 0); }
-    __host__ __device__ __forceinline__ static constexpr int uoff(int j) { return 64 * j + (Ctx::PADU ? ((64 * j) >> LG) : 0); }
-};
-__device__ __forceinline__ bool al16(const void *p, long ld) { return ((unsigned long long)p % 16 == 0) && (ld % 2 == 0); }
-
-// rows 2u, 2u+1 of the column pair starting at g (16-byte aligned): (a.x, a.y) = row 2u, (b.x, b.y) = row 2u+1
-__device__ __forceinline__ void ld_pair(const double *g, long ld, int u, int n, bool c0, bool c1, double2 &a, double2 &b)
-{
-    a = b = d2(0.0, 0.0);
-    const int r = 2 * u;
-    if (!c0) return;
-    if (r < n) {
-        if (c1) a = __ldg(reinterpret_cast<const double2 *>(g + (long)r * ld));
-        else a.x = __ldg(g + (long)r * ld);
-    }
-    if (r + 1 < n) {
-        if (c1) b = __ldg(reinterpret_cast<const double2 *>(g + (long)(r + 1) * ld));
-        else b.x = __ldg(g + (long)(r + 1) * ld);
-    }
-}
+// COL data movement is the 8-byte form only: all cooperative operators (LOAD / STORE / AXPY / LINCOMB) use the SAME
+// thread <-> (row, column) map (ColMap), so consecutive cooperative operators need no barrier between them -- every
+// thread only meets elements it wrote itself.  (A 16-byte form with a second map -- 2 x 2 blocks per thread -- was
+// measured: no gain, the 64-byte row pieces bound the column passes; and mixing two maps without a barrier is a race.)
 
 // ------------------------------------------------------------------------------------------------
 // LOAD: buffer <- elements [0, n) of the operand, zero beyond
@@ -196,26 +170,6 @@ __device__ __forceinline__ void op_load(const Ctx &c, const pde_pass_ins &I)
             if (!one && bytes) src = elem_addr<false>(I, seg_of(I, 2 * c.lane + 64 * k), c.q, 2 * c.lane + 64 * k);
             pcp16(dst + RowMap<Ctx>::off(k), bytes ? src : p0, bytes);
         }
-    } else if (Ctx::W >= 2 && one && al16(I.p[0], I.ld[0])) {
-        const Col16<Ctx> m;
-        const int qc = c.q0 + 2 * m.cp;
-        const bool c0 = qc < c.nseq, c1 = qc + 1 < c.nseq;
-        const long ld0 = I.ld[0];
-        const double *g = reinterpret_cast<const double *>(I.p[0]) + qc;
-        double2 *b0 = c.all + (2 * m.cp) * Ctx::BUFU + m.ubase(), *b1 = b0 + Ctx::BUFU;
-#pragma unroll 1
-        for (int j0 = 0; j0 < Col16<Ctx>::STEPS; j0 += PB) {
-            double2 ra[PB], rb[PB];
-#pragma unroll
-            for (int e = 0; e < PB; ++e) ld_pair(g, ld0, m.rq + 64 * (j0 + e), (j0 + e < Col16<Ctx>::STEPS) ? n : 0, c0, c1, ra[e], rb[e]);
-#pragma unroll
-            for (int e = 0; e < PB; ++e)
-                if (j0 + e < Col16<Ctx>::STEPS && m.rq + 64 * (j0 + e) < Ctx::NUP) {
-                    b0[Col16<Ctx>::uoff(j0 + e)] = d2(ra[e].x, rb[e].x);
-                    b1[Col16<Ctx>::uoff(j0 + e)] = d2(ra[e].y, rb[e].y);
-                }
-        }
-        return;
     } else {
         const ColMap<Ctx> cm;
         double *dst = reinterpret_cast<double *>(c.all + cm.col * Ctx::BUFU) + cm.base();
@@ -304,38 +258,6 @@ __device__ __forceinline__ void op_store(const Ctx &c, const pde_pass_ins &I)
             }
         }
         __syncwarp();
-    } else if (Ctx::W >= 2 && one && !only && al16(I.p[0], I.ld[0])) {
-        const Col16<Ctx> m;
-        const int qc = c.q0 + 2 * m.cp;
-        const bool c0 = qc < c.nseq, c1 = qc + 1 < c.nseq;
-        if (!c0) return;
-        const long ld0 = I.ld[0];
-        double *g = const_cast<double *>(reinterpret_cast<const double *>(I.p[0])) + qc;
-        const double2 *b0 = c.all + (2 * m.cp) * Ctx::BUFU + m.ubase(), *b1 = b0 + Ctx::BUFU;
-#pragma unroll 1
-        for (int j0 = 0; j0 < Col16<Ctx>::STEPS; j0 += PB) {
-            double2 v0[PB], v1[PB];
-#pragma unroll
-            for (int e = 0; e < PB; ++e)
-                if (j0 + e < Col16<Ctx>::STEPS && m.rq + 64 * (j0 + e) < Ctx::NUP) {
-                    v0[e] = b0[Col16<Ctx>::uoff(j0 + e)];
-                    v1[e] = b1[Col16<Ctx>::uoff(j0 + e)];
-                }
-#pragma unroll
-            for (int e = 0; e < PB; ++e) {
-                const int r = 2 * (m.rq + 64 * (j0 + e));
-                if (j0 + e < Col16<Ctx>::STEPS) {
-                    if (r < n) {
-                        if (c1) *reinterpret_cast<double2 *>(g + (long)r * ld0) = d2(v0[e].x, v1[e].x);
-                        else g[(long)r * ld0] = v0[e].x;
-                    }
-                    if (r + 1 < n) {
-                        if (c1) *reinterpret_cast<double2 *>(g + (long)(r + 1) * ld0) = d2(v0[e].y, v1[e].y);
-                        else g[(long)(r + 1) * ld0] = v0[e].y;
-                    }
-                }
-            }
-        }
     } else {
         const ColMap<Ctx> cm;
         if (c.q0 + cm.col >= c.nseq || (only && c.seq0 + c.q0 + cm.col != I.off[0])) return;
@@ -413,30 +335,6 @@ __device__ __forceinline__ void axpy_impl(const Ctx &c, const pde_pass_ins &I)
             }
         }
         __syncwarp();
-    } else if (!STEN && Ctx::W >= 2 && one && al16(I.p[0], I.ld[0])) {
-        const Col16<Ctx> m;
-        const int qc = c.q0 + 2 * m.cp;
-        const bool c0 = qc < c.nseq, c1 = qc + 1 < c.nseq;
-        if (!c0) return;
-        const long ld0 = I.ld[0];
-        const double *g = reinterpret_cast<const double *>(I.p[0]) + qc;
-        double2 *b0 = c.all + (2 * m.cp) * Ctx::BUFU + m.ubase(), *b1 = b0 + Ctx::BUFU;
-#pragma unroll 1
-        for (int j0 = 0; j0 < Col16<Ctx>::STEPS; j0 += PB) {
-            double2 ra[PB], rb[PB];
-#pragma unroll
-            for (int e = 0; e < PB; ++e) ld_pair(g, ld0, m.rq + 64 * (j0 + e), (j0 + e < Col16<Ctx>::STEPS) ? n : 0, c0, c1, ra[e], rb[e]);
-#pragma unroll
-            for (int e = 0; e < PB; ++e) {
-                const int u = m.rq + 64 * (j0 + e);
-                if (j0 + e < Col16<Ctx>::STEPS && u < Ctx::NUP && (scaled || 2 * u < n)) {
-                    double2 &x0 = b0[Col16<Ctx>::uoff(j0 + e)], &x1 = b1[Col16<Ctx>::uoff(j0 + e)];
-                    const double2 g0 = d2(ra[e].x, rb[e].x), g1 = d2(ra[e].y, rb[e].y);
-                    x0 = scaled ? d2(fma(f0, g0.x, f1 * x0.x), fma(f0, g0.y, f1 * x0.y)) : fmas(f0, g0, x0);
-                    x1 = scaled ? d2(fma(f0, g1.x, f1 * x1.x), fma(f0, g1.y, f1 * x1.y)) : fmas(f0, g1, x1);
-                }
-            }
-        }
     } else {
         const ColMap<Ctx> cm;
         if (c.q0 + cm.col >= c.nseq) return;
@@ -484,13 +382,6 @@ __device__ __forceinline__ void op_axpy(const Ctx &c, const pde_pass_ins &I)
 // start[k] valid elements each (zero beyond); flag ACCUM keeps the buffer.  All K loads of a batch are in
 // flight together (the right-hand sides of the Helmholtz problems are sums of 3-5 arrays).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool lincomb_al16(const pde_pass_ins &I, int K)
-{
-    bool ok = true;
-    for (int k = 0; k < K; ++k) ok = ok && al16(I.p[k], I.ld[k]);
-    return ok;
-}
-
 template <bool COL, class Ctx>
 __device__ __forceinline__ void op_lincomb(const Ctx &c, const pde_pass_ins &I)
 {
@@ -536,49 +427,6 @@ __device__ __forceinline__ void op_lincomb(const Ctx &c, const pde_pass_ins &I)
             }
         }
         __syncwarp();
-    } else if (Ctx::W >= 2 && lincomb_al16(I, K)) {
-        constexpr int VB = 2;
-        const Col16<Ctx> m;
-        const int qc = c.q0 + 2 * m.cp;
-        const bool c0 = qc < c.nseq, c1 = qc + 1 < c.nseq;
-        if (!c0) return;
-        double2 *b0 = c.all + (2 * m.cp) * Ctx::BUFU + m.ubase(), *b1 = b0 + Ctx::BUFU;
-        const double *gk[KMAX];
-        long ldk[KMAX];
-        int nk[KMAX];
-        double cf[KMAX];
-#pragma unroll
-        for (int k = 0; k < KMAX; ++k) {
-            ldk[k] = k < K ? I.ld[k] : 0;
-            gk[k] = k < K ? reinterpret_cast<const double *>(I.p[k]) + qc : nullptr;
-            nk[k] = k < K ? I.start[k] : 0;
-            cf[k] = k < K ? I.coef[k] : 0.0;
-        }
-#pragma unroll 1
-        for (int j0 = 0; j0 < Col16<Ctx>::STEPS; j0 += VB) {
-            double2 ra[VB][KMAX], rb[VB][KMAX];
-#pragma unroll
-            for (int e = 0; e < VB; ++e)
-#pragma unroll
-                for (int k = 0; k < KMAX; ++k)
-                    ld_pair(gk[k], ldk[k], m.rq + 64 * (j0 + e), (k < K && j0 + e < Col16<Ctx>::STEPS) ? nk[k] : 0, c0, c1, ra[e][k],
-                            rb[e][k]);
-#pragma unroll
-            for (int e = 0; e < VB; ++e) {
-                const int u = m.rq + 64 * (j0 + e);
-                if (j0 + e < Col16<Ctx>::STEPS && u < Ctx::NUP) {
-                    double2 &x0 = b0[Col16<Ctx>::uoff(j0 + e)], &x1 = b1[Col16<Ctx>::uoff(j0 + e)];
-                    double2 a0 = accum ? x0 : d2(0.0, 0.0), a1 = accum ? x1 : d2(0.0, 0.0);
-#pragma unroll
-                    for (int k = 0; k < KMAX; ++k) {
-                        a0 = fmas(cf[k], d2(ra[e][k].x, rb[e][k].x), a0);
-                        a1 = fmas(cf[k], d2(ra[e][k].y, rb[e][k].y), a1);
-                    }
-                    x0 = a0;
-                    x1 = a1;
-                }
-            }
-        }
     } else {
         const ColMap<Ctx> cm;
         if (c.q0 + cm.col >= c.nseq) return;

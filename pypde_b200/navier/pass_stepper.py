@@ -65,7 +65,7 @@ class PassStepper(FastStepper):
         even leading dimensions; rows whose byte length is a multiple of 2 KB get 64 bytes of padding like in
         FastStepper (column walks of the x-transforms)."""
         nm = len(self.runs)
-        ld = cols
+        ld = cols + (cols & 1)      # 16-byte aligned rows: the DCT row kernel stages them with bulk copies
         if not exact:
             assert cols % 2 == 0
             ld = cols + 8 if cols % 256 == 0 else cols
@@ -90,7 +90,8 @@ class PassStepper(FastStepper):
         for name in ("e3", "f3", "g3", "rest3", "conv"):
             give(name, N0, N1, 3)
         give("dpdx", N0, N1)
-        # transforms: D x D arrays may have odd widths (3073): exact pitch, only the DCT / product kernels touch them
+        # transforms: D x D arrays may have odd widths (3073): pitch rounded up to even, only the DCT / product kernels
+        # touch them (the products run over the padded rows as one contiguous range: the pad column stays zero)
         give("X8", D0, N1, 8)
         give("phys", D0, D1, 6, exact=True)
         give("uwa", D0, D1, 2, exact=True)
@@ -113,7 +114,9 @@ class PassStepper(FastStepper):
         ns = self.ns
         self.tbc_cheby = C.to_dev(ns.Tbc_cheby).contiguous()
         self.dTbcdz2 = C.to_dev(ns.dTbcdz2).contiguous()
-        self.dTbcdz1 = C.to_dev(ns.dTbcdz1).contiguous()
+        d1 = C.to_dev(ns.dTbcdz1)
+        self.dTbcdz1 = torch.zeros((self.D0, self.D1 + (self.D1 & 1)), dtype=torch.float64, device=self.dev)[:, : self.D1]
+        self.dTbcdz1.copy_(d1)      # same pitch as the physical-space arrays
         pp = ns.solver_P.plan_for_lhs[0]
         self.ptab = PS.PoissonTables(pp._plan, PS.lg_for(self.M0))      # grid-only: shared by all members
 
@@ -229,15 +232,16 @@ class PassStepper(FastStepper):
         use_old = c != 0.0
         m0 = self.mb[0]
         new0, old0 = m0.uw[rk % 2], m0.uw[(rk + 1) % 2]
+        ldp = self.D1 + (self.D1 & 1)
         for t in list(new0) + list(old0) + list(m0.phys) + [self.dTbcdz1]:
-            assert t.is_contiguous() and tuple(t.shape) == (self.D0, self.D1)
+            assert tuple(t.shape) == (self.D0, self.D1) and t.stride() == (ldp, 1)
         dxU, dxV, dxT, dzU, dzV, dzT = m0.phys
         pargs = (_ptr(new0[0]), _ptr(new0[1]), _ptr(old0[0]) if use_old else None, _ptr(old0[1]) if use_old else None,
                  _ptr(dxU), _ptr(dzU), _ptr(dxV), _ptr(dzV), _ptr(dxT), _ptr(dzT), _ptr(self.dTbcdz1))
         if len(self.runs) == 1:
-            calls.add(Lb.pde_conv_products, self.D0 * self.D1, b, c, *pargs)
-        else:   # member m's arrays lie D0 * D1 elements after member m-1's (one allocation per array kind)
-            calls.add(Lb.pde_conv_products_members, self.D0 * self.D1, len(self.runs), self.D0 * self.D1, b, c, *pargs)
+            calls.add(Lb.pde_conv_products, self.D0 * ldp, b, c, *pargs)
+        else:   # member m's arrays lie D0 * ldp elements after member m-1's (one allocation per array kind)
+            calls.add(Lb.pde_conv_products_members, self.D0 * ldp, len(self.runs), self.D0 * ldp, b, c, *pargs)
         self._dct_members(calls, self.plan1, ops.FWD, 1, lambda m: list(m.phys[:3]), lambda m: [f[:, : N1] for f in m.F3])
         self._dct_members(calls, self.plan0, ops.FWD, 0, lambda m: [f[:, : N1] for f in m.F3],
                           lambda m: [cv[: N0] for cv in m.conv])

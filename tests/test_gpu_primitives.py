@@ -299,6 +299,38 @@ def test_fft_dct_vs_oracle(dev, L, axis):
         assert rel_l2(tr(H(got)), o.forward(x)[:n_out]) < tol
 
 
+@pytest.mark.parametrize("L", [2049, 3073, 4097])
+def test_fft_dct_rows_persistent_tma(dev, L):
+    """Axis-1 transforms of rows with an even pitch (16-byte aligned rows) run in the persistent kernel whose input
+    rows are staged by the bulk-copy engine (k_dct_row_tma): all modes, odd and even input lengths (the odd tail
+    element travels separately), zero padding, truncation, and more rows than resident CTAs (3 x 148)."""
+    import torch
+    from pypde_b200 import ops
+    from oracle import pypde_port as P
+    rng = np.random.default_rng(L)
+    plan = ops.DctPlan(L, algo=2)
+    o = P.Basis(L, "CH")
+    tol = 5e-15 * np.log2(L)
+    nb = 1000
+    x = rng.standard_normal((nb, L))
+    for n_in in (L, (2 * L) // 3, (2 * L) // 3 + 1, 2, 1):
+        ld = n_in + 2
+        ld += ld & 1                                          # an even pitch > n_in
+        buf = torch.full((nb, ld), float("nan"), dtype=torch.float64, device=dev)     # pad columns must never be read
+        buf[:, :n_in] = T(x[:, :n_in], dev)
+        xin = buf[:, :n_in]
+        assert xin.stride(0) % 2 == 0 and xin.data_ptr() % 16 == 0
+        xp = np.zeros((L, nb))
+        xp[:n_in] = x[:, :n_in].T
+        for mode, ref in ((ops.BWD, lambda a: o.backward(a.copy())), (ops.FWD, o.forward)):
+            if mode == ops.FWD and n_in != L:
+                continue
+            for n_out in (L, (2 * L) // 3 + 1):
+                got = H(ops.dct1(plan, mode, xin, axis=1, n_out=n_out))
+                assert got.shape == (nb, n_out)
+                assert rel_l2(got.T, ref(xp)[:n_out]) < tol, (L, n_in, mode, n_out)
+
+
 def test_fft_dct_roundtrip_full_size(dev):
     """BASELINE-size property: backward(forward(f)) == f on the 3073-point dealias grid."""
     import torch
