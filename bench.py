@@ -185,6 +185,26 @@ def run_reference(args, cfg):
 
 
 # --------------------------------------------------------------------------- GPU arm
+NCU_STAGE_CSV = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_ncu_stage.csv")
+
+
+def ncu_traffic(kernel_substr, path=NCU_STAGE_CSV):
+    """(average dram__bytes_read + dram__bytes_write per launch in bytes, source) of the kernels whose name contains
+    `kernel_substr` in the committed ncu --set full capture of ONE rbc2048 stage (tools/final_round2.sh writes it)."""
+    import csv
+    try:
+        rows = [r for r in csv.reader(l for l in open(path) if not l.startswith('"#')) if r]
+        hdr, units, body = rows[0], rows[1], rows[2:]
+        ir, iw, ik = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("Kernel Name")
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        tot = [float(r[ir]) * scale[units[ir]] + float(r[iw]) * scale[units[iw]] for r in body if kernel_substr in r[ik]]
+        if not tot:
+            return None, None
+        return sum(tot) / len(tot), "profiles/%s (%d launches of one stage)" % (os.path.basename(path), len(tot))
+    except (OSError, ValueError, KeyError, IndexError):
+        return None, None
+
+
 class OpTimer:
     """CUDA-event timer around every C-ABI call of one (eager) time step: wraps the prebuilt launch
     lists of the stepper.  Events are recorded on the stream the kernels are launched on."""
@@ -480,12 +500,18 @@ def run_gpu(args, cfg):
                 "achieved": dct_work / (dct_ms * 1e-3) / 1e9 if dct_ms else None, "peak": peaks.get("hbm_gbs"),
                 "unit": "GB/s",
                 "traffic": None,
-                "traffic_note": "not captured in this run (ncu --set full of the stage: profiles/); algorithmic bytes = "
-                                "8 (n_in + n_out) batch per array: every input element read once, every output element written once",
+                "traffic_note": "algorithmic bytes = 8 (n_in + n_out) batch per array: every input element read once, "
+                                "every output element written once",
                 "peak_source": peak_src, "launches_per_step": dct_launches,
                 "avg_launch_ms": dct_ms / max(dct_launches, 1), "share_of_step": dct_ms / step_ms_instr,
                 "algorithmic_bytes_per_launch": dct_work / max(dct_launches, 1)}
     roof_dct["frac"] = roof_dct["achieved"] / roof_dct["peak"] if roof_dct["achieved"] else None
+    if not slab and tuple(cfg["shape"]) == (2048, 2048):
+        # DRAM bytes per launch of the same kernels from the committed ncu --set full capture of one stage
+        roof_dct["traffic"], roof_dct["traffic_source"] = ncu_traffic("k_dct")
+        roof_gemm_traffic = ncu_traffic("k_gemm")
+    else:
+        roof_gemm_traffic = (None, None)
     roof_gemm = {"kernel": "k_gemm_f64 (DMMA; Poisson projections Hy, Qy)", "bound": "tensor",
                  "achieved": gemm["work"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] else None, "peak": fp64_peak,
                  "unit": "TFLOP/s", "traffic": None,
@@ -493,6 +519,8 @@ def run_gpu(args, cfg):
                  "launches_per_step": gemm["launches"], "avg_launch_ms": gemm["ms"] / max(gemm["launches"], 1),
                  "share_of_step": gemm["ms"] / step_ms_instr}
     roof_gemm["frac"] = roof_gemm["achieved"] / fp64_peak if roof_gemm["achieved"] else None
+    if roof_gemm_traffic[0]:
+        roof_gemm["traffic"], roof_gemm["traffic_source"] = roof_gemm_traffic
     roof = roof_dct if dct_ms >= gemm["ms"] else roof_gemm
     roof_other = roof_gemm if roof is roof_dct else roof_dct
 
