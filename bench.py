@@ -496,7 +496,7 @@ def run_gpu(args, cfg):
     dct_work = sum(v["work"] for k, v in ops_ms.items() if k.startswith("pde_dct1"))
     dct_launches = sum(v["launches"] for k, v in ops_ms.items() if k.startswith("pde_dct1"))
     gemm = ops_ms.get("pde_gemm_f64", {"ms": 0.0, "work": 0.0, "launches": 1})
-    roof_dct = {"kernel": "k_dct_fft_t (shared-memory FFT DCT-I, all batched transforms of the step)", "bound": "hbm",
+    roof_dct = {"kernel": "k_dct_row_tma + k_dct_fft_t (shared-memory FFT DCT-I: persistent TMA-staged rows, 4-column strips; all batched transforms of the step)", "bound": "hbm",
                 "achieved": dct_work / (dct_ms * 1e-3) / 1e9 if dct_ms else None, "peak": peaks.get("hbm_gbs"),
                 "unit": "GB/s",
                 "traffic": None,

@@ -128,6 +128,24 @@ struct SeqPad {
         (AXIS != 0 || S <= 1 || 8 % S != 0) ? 0 : ((8 / (S > 0 ? S : 1) - (P + P / M1) % 8) % 8 + 8) % 8;
 };
 
+// Register cap: what the CTAs that fit an SM by shared memory (at most 3) can share.  Registers are granted
+// per warp in coarse units (ncu: a 106-register kernel = 3392 per warp was limited to TWO 6-warp CTAs, i.e. it
+// was charged 4096), so the cap is rounded down to a multiple of 32 per thread: 96 is what lets three
+// 192-thread CTAs run together.  Never below 96 (the radix-16 butterfly needs ~100): fewer CTAs instead.
+constexpr int fft_regs(int ctas, int T)
+{
+    const int per_thread = 65536 / (ctas * (T / 32)) / 1024 * 1024 / 32;
+    return per_thread > 168 ? 168 : per_thread;
+}
+template <int P, int S, int T, int R1>
+struct FftRegs {
+    static constexpr int SMEM = S * Pad<P, P / R1, 7>::SEQ * 16 + 1024;
+    static constexpr int FIT = 227 * 1024 / SMEM;
+    static constexpr int C3 = FIT < 1 ? 1 : (FIT > 3 ? 3 : FIT);
+    static constexpr int CTAS = fft_regs(C3, T) >= 96 ? C3 : (C3 > 1 && fft_regs(C3 - 1, T) >= 96 ? C3 - 1 : 1);
+    static constexpr int value = fft_regs(CTAS, T);
+};
+
 // Twiddles of a DIF pass.  WOFF < 0: the plain table W[t] = exp(-2 pi i t / P), read with stride (Bluestein
 // kernels).  WOFF >= 0: per-pass tables laid out [r][j] (entry (r - 1) * M + j = W_NCUR^{j r}) starting at
 // W + WOFF: consecutive lanes (consecutive j) read consecutive entries.  ncu on the strided version showed the
@@ -144,6 +162,30 @@ struct SeqPad {
 // butterfly loads only w^1, w^2, w^3, w^4, w^8, w^12 and forms the other nine as products w^{4q} w^b (9 complex
 // multiplications instead of 9 16-byte L1 requests per thread: the kernels are L1TEX-bound, the fp64 pipe is 30 % busy).
 // The products carry one more rounding (<= 1.5 ulp instead of 0.5 ulp per twiddle).
+// Number of twiddles of a radix-16 butterfly that are requested BEFORE its inputs are read and transformed (the
+// rest are requested while the first ones are multiplied).  ncu's source view of the 96-register row kernel showed
+// every twiddle load issued a few instructions before its use: 30 % of all stall samples were long-scoreboard
+// waits in the complex multiplications (the 46 KB first-pass table does not stay in the ~28 KB of L1 left next to
+// 222 KB of shared memory).  Measured on the rbc2048 step (axis-1 DCT time per step): 0 early twiddles 2.23 ms,
+// 3: 2.18, 4: 2.11, 5: 2.12, 6: 2.23 (spills).  Also tried: prefetch.global.L1 of all 15 lines while the row is in
+// flight (2.19), and finishing / multiplying / storing the outputs in four groups with the next group's twiddles
+// requested one group ahead (2.19).
+#ifndef PDE_FFT_TWPRE
+#define PDE_FFT_TWPRE 4
+#endif
+template <int R>
+struct TwPre {
+    static constexpr int N = (R == 16 && PDE_FFT_TWPRE > 0) ? PDE_FFT_TWPRE : 0;
+};
+
+// a_r *= w^r, r = 1 .. R-1; the first TwPre<R>::N twiddles come from `pre` (loaded by the caller ahead of the butterfly)
+template <int R, int NP, class LD>
+__device__ __forceinline__ void twiddle_mul_pre(double2 *a, const double2 *pre, LD ld)
+{
+#pragma unroll
+    for (int r = 1; r < R; ++r) a[r] = cmul(a[r], r <= NP ? pre[r - 1] : ld(r));
+}
+
 template <int R, class LD>
 __device__ __forceinline__ void twiddle_mul(double2 *a, LD ld)
 {
@@ -224,11 +266,19 @@ __device__ __forceinline__ void dif_pass_t(double2 *z, const double2 *__restrict
         }
         double2 *p = z + s * PS + off;
         double2 a[R];
+        auto ldw = [&](int r) { return WOFF < 0 ? __ldg(W + j * (r * TWS)) : __ldg(W + WOFF + (r - 1) * M + j); };
+        // (all 15 early in the 160-register axis-0 kernels: measured 2.06 ms instead of 2.03 per step -- no gain there)
+        constexpr int NPRE = (M > 1 && WOFF >= 0) ? TwPre<R>::N : 0;
+        double2 pre[NPRE > 0 ? NPRE : 1];
+#pragma unroll
+        for (int r = 1; r <= NPRE; ++r) pre[r - 1] = ldw(r);
 #pragma unroll
         for (int r = 0; r < R; ++r) a[r] = p[r * RS];
         dft<R>(a);
-        if (M > 1)
-            twiddle_mul<R>(a, [&](int r) { return WOFF < 0 ? __ldg(W + j * (r * TWS)) : __ldg(W + WOFF + (r - 1) * M + j); });
+        if (M > 1) {
+            if constexpr (NPRE > 0) twiddle_mul_pre<R, NPRE>(a, pre, ldw);
+            else twiddle_mul<R>(a, ldw);
+        }
 #pragma unroll
         for (int r = 0; r < R; ++r) p[r * RS] = a[r];
     }
@@ -289,24 +339,6 @@ struct DigitRev {
         if constexpr (sizeof...(Rest) > 0) return (k % R) * n + DigitRev<n, Rest...>::pos(k / R);
         else return (k % R) * n;
     }
-};
-
-// Register cap: what the CTAs that fit an SM by shared memory (at most 3) can share.  Registers are granted
-// per warp in coarse units (ncu: a 106-register kernel = 3392 per warp was limited to TWO 6-warp CTAs, i.e. it
-// was charged 4096), so the cap is rounded down to a multiple of 32 per thread: 96 is what lets three
-// 192-thread CTAs run together.  Never below 96 (the radix-16 butterfly needs ~100): fewer CTAs instead.
-constexpr int fft_regs(int ctas, int T)
-{
-    const int per_thread = 65536 / (ctas * (T / 32)) / 1024 * 1024 / 32;
-    return per_thread > 168 ? 168 : per_thread;
-}
-template <int P, int S, int T, int R1>
-struct FftRegs {
-    static constexpr int SMEM = S * Pad<P, P / R1, 7>::SEQ * 16 + 1024;
-    static constexpr int FIT = 227 * 1024 / SMEM;
-    static constexpr int C3 = FIT < 1 ? 1 : (FIT > 3 ? 3 : FIT);
-    static constexpr int CTAS = fft_regs(C3, T) >= 96 ? C3 : (C3 > 1 && fft_regs(C3 - 1, T) >= 96 ? C3 - 1 : 1);
-    static constexpr int value = fft_regs(CTAS, T);
 };
 
 template <int P, int S, int T, int AXIS, int... RAD>
@@ -575,7 +607,7 @@ k_dct_row_tma(const double2 *__restrict__ W, const double2 *__restrict__ CS, int
               long ldy, int n_out, int batch, int nitems)
 {
     static_assert(FirstRadix<RAD...>::value == 16 && T == P / 16, "one radix-16 first-pass butterfly per thread");
-    extern __shared__ __align__(128) double2 zsm[];
+    extern __shared__ __align__(16) double2 zsm[];
     constexpr int R = 16, M = P / R, H = P / 2;
     using PD = Pad<P, M, 0>;
     constexpr int PS = PD::SEQ, RAWN = P + 2;
@@ -609,6 +641,10 @@ k_dct_row_tma(const double2 *__restrict__ W, const double2 *__restrict__ CS, int
     for (int item = blockIdx.x; item < nitems; item += gridDim.x, phase ^= 1u) {
         const int job = item / batch, q = item - job * batch;
         double *__restrict__ yrow = ptrs.y[job] + (long)q * ldy;
+        auto ldw1 = [&](int r) { return __ldg(W + (r - 1) * M + j); };
+        double2 pre1[TwPre<R>::N > 0 ? TwPre<R>::N : 1];       // requested while the row is still in flight
+#pragma unroll
+        for (int r = 1; r <= TwPre<R>::N; ++r) pre1[r - 1] = ldw1(r);
         mbar_wait(bar, phase);
         // ---- first pass: z_m = (e_2m, e_2m+1), m = j + r M; m < H: (x_2m, x_2m+1); m >= H: (x_{2P-2m}, x_{2P-2m-1})
         double2 a[R];
@@ -635,7 +671,8 @@ k_dct_row_tma(const double2 *__restrict__ W, const double2 *__restrict__ CS, int
             a[r] = make_double2(v0 * (edge ? 1.0 : se), v1 * so);
         }
         dft<R>(a);
-        twiddle_mul<R>(a, [&](int r) { return __ldg(W + (r - 1) * M + j); });
+        if constexpr (TwPre<R>::N > 0) twiddle_mul_pre<R, TwPre<R>::N>(a, pre1, ldw1);
+        else twiddle_mul<R>(a, ldw1);
         {
             double2 *p = zsm + j;
 #pragma unroll
