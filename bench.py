@@ -318,7 +318,43 @@ def run_ensemble(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = sampler.stop()
+    # ---- end to end: every member's state uploaded from pinned host memory before and read back after each step ----
+    state = [t for m in ens.members for t in (m.T.vhat, m.U.vhat, m.V.vhat, m.pres.vhat)]
+    host_a = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True).copy_(t) for t in state]
+    host_b = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in state]
+    h2d = d2h = sum(h.numel() * 8 for h in host_a)
+    e2e_steps = max(1, min(args.steps, 5))
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        for h, t in zip(host_a, state):
+            t.copy_(h, non_blocking=True)
+        ens.update()
+        for h, t in zip(host_b, state):
+            h.copy_(t, non_blocking=True)
+        torch.cuda.synchronize()
+        host_a, host_b = host_b, host_a
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms, float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t)
+        e2e_ms, h2d, d2h = float(tm[0].item()), int(t[1].item()), int(t[2].item())
     finite = all(bool(torch.isfinite(m.T.vhat).all()) for m in ens.members)
+    # whole step against the SURVEY 8(d) axis-pass model (all members): small grids, dense-matrix transforms
+    peaks, peak_src = measured_peaks()
+    N, D, M = 128, 193, 126
+    stage_bytes = 8 * (31 * M * M + 18 * M * N + 5 * N * N + 12 * D * M + 6 * D * N + D * D)
+    alg = stage_bytes * 3 * ENSEMBLE["members"]
+    achieved = alg / (ms / args.steps * 1e-3) / 1e9
+    roof = {"kernel": "whole ensemble step (45 launches: k_pass, batched k_gemm_f64 for the dense DCTs / projections, "
+                      "k_conv_products_members)", "bound": "hbm", "achieved": achieved,
+            "peak": peaks.get("hbm_gbs") * world, "unit": "GB/s", "frac": achieved / (peaks.get("hbm_gbs") * world),
+            "traffic": None, "peak_source": peak_src,
+            "note": "algorithmic bytes of the SURVEY.md 8(d) axis-pass model x 256 members; per-kernel view: tools/prof_ensemble.py"}
     # launches: one eager member step counted through the library, times members and steps
     m0 = ens.members[0]
     _cabi.launch_count_reset()
@@ -355,6 +391,9 @@ def run_ensemble(args):
                        "l2": "one member's working set fits L2 (small-grid regime by design)", "finite": finite,
                        "setup_s": setup_s, "cuda_graph": True},
             "member_steps_per_sec": args.steps * ENSEMBLE["members"] / (ms * 1e-3),
+            "e2e": {"value": 1e3 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "roofline": roof,
             "clocks": clocks, "gpu_launches": int(launches_step * args.steps),
             "gpu_launches_per_ensemble_step": int(launches_step), "batched": bool(ens.batched),
             "gpu_launches_per_member_step": per_member, "cpu_baseline": cpu}
@@ -734,7 +773,9 @@ def run_dct(args):
         b = Base(N, "CH")
         batch = max(1000, min(1_000_000, (1 << 27) // N))       # ~1 GB per array: larger than L2
         x = torch.randn((N, batch), dtype=torch.float64, device="cuda")
-        xt = x.T.contiguous()
+        # rows with an even pitch (16-byte aligned rows, what the stepper allocates): odd N gets one pad column
+        xt = torch.zeros((batch, N + (N & 1)), dtype=torch.float64, device="cuda")[:, :N]
+        xt.copy_(x.T)
         for name, fn, arr, axis in (("fwd0", b.forward_fft, x, 0), ("bwd0", b.backward_fft, x, 0),
                                     ("fwd1", b.forward_fft, xt, 1), ("bwd1", b.backward_fft, xt, 1)):
             cases.append((N, batch, b.plan.algo, name, fn, arr, axis))

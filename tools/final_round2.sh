@@ -14,5 +14,7 @@ timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none -c
 # one eager stage (15 launches) after 3 warm-up steps = 135 launches of our kernels
 timeout -s KILL 900 ncu --set full --clock-control none -k regex:"k_pass|k_dct|k_gemm|k_conv" -s 135 -c 15 -o /tmp/ncu_stage_r2 -f python bench.py --steps 1 --warmup 3 --no-graph --no-cpu-baseline > $O/ncu_stage_r2.log 2>&1
 ncu -i /tmp/ncu_stage_r2.ncu-rep --page raw --csv > $O/ncu_stage_r2_raw.csv 2>/dev/null
+python tools/summarise_ncu.py raw $O/ncu_stage_r2_raw.csv $O/r02_ncu_stage.csv "ncu --set full --clock-control none -k regex:k_pass|k_dct|k_gemm|k_conv -s 135 -c 15 python bench.py --steps 1 --warmup 3 --no-graph (ONE eager rbc2048 RK3 stage of the round-2 stepper: 15 launches in order PX1 PY2 DCTx DCTy products DCTy DCTx PX3 PY4 PX5 GEMM PX6 GEMM PY7 PX8; per-launch, cold cache, serialised)"
+python tools/summarise_ncu.py list $O/launches_r2_rbc2048.csv $O/r02_ncu_launches_rbc2048_summary.csv "ncu --metrics gpu__time_duration.sum --clock-control none -c 300 python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline (round 2, PassStepper: 15 launches per stage; first 300 launches: warm-up + timed steps; cold-cache serialised: compare SHARES)"
 python tools/bench_pass.py 2048 > $O/bench_pass_r2.json 2> $O/bench_pass_r2.err
 grep -E "passed|failed|rc=|^FAILED" $O/pytest_gpu_r2.log | tail -4; tail -2 $O/smoke_r2.log; for f in $O/bench_r2_*.json; do head -c 200 $f; echo; done; du -sh $O
