@@ -7,7 +7,7 @@
 //
 // CTA tile (8 MI WM) x (8 NI WN) x 16 with 8 warps laid out WM x WN, warp tile = MI x NI DMMA tiles
 // (128 x 64 = 4 x 2 warps of 4 x 4 tiles; 128 x 56 = 8 x 1 warps of 2 x 7 tiles; 64 x 64; 32 x 64),
-// 3-stage cp.async ring in shared memory; smem rows are padded so that the
+// cp.async ring in shared memory (BK = 32, 2 stages); smem rows are padded so that the
 // 64-bit fragment loads of a half-warp hit 16 distinct bank pairs.  The tile shape is chosen per
 // problem to fill whole waves of 2 CTAs per SM: the Poisson projections of rbc2048 (2046 x 2046) are
 // 512 tiles of 128 x 64 = 1.73 waves on 148 SMs, but 592 tiles of 128 x 56 = exactly 2 waves (-12 %).
@@ -19,7 +19,16 @@
 
 namespace pde {
 
-constexpr int BN = 64, BK = 16, STAGES = 3;   // BM = 32 * MI (MI m-tiles of 8 rows per warp, 4 warps along M)
+// K depth of a shared-memory tile and depth of the cp.async ring.  Two CTAs per SM must fit (<= 113 KB each).
+// Measured on the two 2046 x 2046 x 2048 projections of an rbc2048 stage (ms per step, 6 products):
+// BK 16 x 3 stages 3.677, BK 8 x 4: 3.53, BK 8 x 5: 3.56, BK 32 x 2: 3.476 (half the barriers per flop; 110 KB).
+#ifndef PDE_GEMM_BK
+#define PDE_GEMM_BK 32
+#endif
+#ifndef PDE_GEMM_STAGES
+#define PDE_GEMM_STAGES 2
+#endif
+constexpr int BN = 64, BK = PDE_GEMM_BK, STAGES = PDE_GEMM_STAGES;   // BM = 32 * MI (MI m-tiles of 8 rows per warp, 4 warps along M)
 constexpr int APITCH = BK + 4;           // doubles per smem row of an (rows x BK) tile
 constexpr int BPITCH_NN = BN + 4;        // doubles per smem row of the (BK x BN) tile
 constexpr int A_TILE_MAX = 128 * APITCH;      // doubles

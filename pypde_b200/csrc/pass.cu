@@ -809,6 +809,10 @@ __device__ __forceinline__ void op_rec2(const Ctx &c, const pde_pass_ins &I)
     __syncwarp();
 }
 
+// (Measured and removed: prefetch.global.L2 of the row pieces that the later cooperative operators of a COL strip and
+// the first operator of the CTA's next strip will read -- COL phases run in lock step, HBM idles while a strip
+// computes -- changed nothing: 2.42 -> 2.46 ms of column passes per rbc2048 step.  The column passes are bound by
+// the dependent chains of the per-warp recurrences with 8 warps per SM, not by the latency of their loads.)
 // Short sequences are latency-bound per strip (a handful of dependent memory round trips, little arithmetic): two
 // CTAs per SM (128 registers) instead of one (prof of the 256-member 128^2 ensemble: 25 us per strip with one).
 template <bool COL, int LG>
