@@ -22,6 +22,7 @@ namespace pde {
 // K depth of a shared-memory tile and depth of the cp.async ring.  Two CTAs per SM must fit (<= 113 KB each).
 // Measured on the two 2046 x 2046 x 2048 projections of an rbc2048 stage (ms per step, 6 products):
 // BK 16 x 3 stages 3.677, BK 8 x 4: 3.53, BK 8 x 5: 3.56, BK 32 x 2: 3.476 (half the barriers per flop; 110 KB).
+// (256 x 56 tiles, one 8-warp CTA per SM with 202 registers, fewer fragment loads per DMMA: 3.93 -- 16 warps per SM matter.)
 #ifndef PDE_GEMM_BK
 #define PDE_GEMM_BK 32
 #endif
