@@ -201,3 +201,21 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"] == "rbc64"
+
+
+def test_bench_traffic_from_committed_ncu_capture():
+    """`roofline.traffic` of the bench line is read from the committed ncu --set full capture of one stage: the
+    parser finds the four transform launches and the two projections of a stage, and the transforms' DRAM bytes
+    per launch agree with the algorithmic bytes 8 (n_in + n_out) batch (nothing re-read: within 15 %)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    dct, src = bench.ncu_traffic("k_dct")
+    gemm, _ = bench.ncu_traffic("k_gemm")
+    assert src and "4 launches" in src and dct > 0 and gemm > 0
+    N, D = 2048, 3073
+    alg = 8.0 * ((N + D) * 8 * N + (N + D) * 8 * D + (D + N) * 3 * D + (D + N) * 3 * N) / 4     # per launch
+    assert abs(dct - alg) / alg < 0.15, (dct, alg)
+    assert bench.ncu_traffic("no_such_kernel") == (None, None)
+    assert bench.ncu_traffic("k_dct", path=os.path.join(ROOT, "profiles", "missing.csv")) == (None, None)
