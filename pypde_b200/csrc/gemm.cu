@@ -7,7 +7,7 @@
 //
 // CTA tile (8 MI WM) x (8 NI WN) x 16 with 8 warps laid out WM x WN, warp tile = MI x NI DMMA tiles
 // (128 x 64 = 4 x 2 warps of 4 x 4 tiles; 128 x 56 = 8 x 1 warps of 2 x 7 tiles; 64 x 64; 32 x 64),
-// cp.async ring in shared memory (BK = 32, 2 stages); smem rows are padded so that the
+// cp.async ring in shared memory (K depth 32 x 2 stages or 16 x 3, chosen per launch); smem rows are padded so that the
 // 64-bit fragment loads of a half-warp hit 16 distinct bank pairs.  The tile shape is chosen per
 // problem to fill whole waves of 2 CTAs per SM: the Poisson projections of rbc2048 (2046 x 2046) are
 // 512 tiles of 128 x 64 = 1.73 waves on 148 SMs, but 592 tiles of 128 x 56 = exactly 2 waves (-12 %).
@@ -19,22 +19,22 @@
 
 namespace pde {
 
-// K depth of a shared-memory tile and depth of the cp.async ring.  Two CTAs per SM must fit (<= 113 KB each).
-// Measured on the two 2046 x 2046 x 2048 projections of an rbc2048 stage (ms per step, 6 products):
-// BK 16 x 3 stages 3.677, BK 8 x 4: 3.53, BK 8 x 5: 3.56, BK 32 x 2: 3.476 (half the barriers per flop; 110 KB).
+// K depth BK of a shared-memory tile and depth of the cp.async ring: template parameters, two configurations.
+// Two CTAs per SM must fit (<= 113 KB each).  Measured on the 2046 x 2046 x 2048 projections of rbc2048 (ms per
+// step, 6 products): BK 16 x 3 stages 3.677, 8 x 4: 3.53, 8 x 5: 3.56, 32 x 2: 3.476 (half the barriers per flop) -- but
+// on the row slabs of the multi-GPU path (1024 / 512 rows: ONE wave of tiles, all CTAs start together) the deeper
+// ring wins: 16 x 3 1.95 / 1.15 ms, 32 x 2 2.16 / 1.20 ms.  So: 32 x 2 for launches of two or more waves, else 16 x 3.
 // (256 x 56 tiles, one 8-warp CTA per SM with 202 registers, fewer fragment loads per DMMA: 3.93 -- 16 warps per SM matter.)
-#ifndef PDE_GEMM_BK
-#define PDE_GEMM_BK 32
-#endif
-#ifndef PDE_GEMM_STAGES
-#define PDE_GEMM_STAGES 2
-#endif
-constexpr int BN = 64, BK = PDE_GEMM_BK, STAGES = PDE_GEMM_STAGES;   // BM = 32 * MI (MI m-tiles of 8 rows per warp, 4 warps along M)
-constexpr int APITCH = BK + 4;           // doubles per smem row of an (rows x BK) tile
-constexpr int BPITCH_NN = BN + 4;        // doubles per smem row of the (BK x BN) tile
-constexpr int A_TILE_MAX = 128 * APITCH;      // doubles
-constexpr int B_TILE = (BN * APITCH > BK * BPITCH_NN) ? BN * APITCH : BK * BPITCH_NN;
-constexpr int GEMM_SMEM = STAGES * (A_TILE_MAX + B_TILE) * 8;
+constexpr int BN = 64;                         // BM = 32 * MI (MI m-tiles of 8 rows per warp, 4 warps along M)
+constexpr int BPITCH_NN = BN + 4;              // doubles per smem row of the (BK x BN) tile
+template <int BK>
+struct KTile {
+    static constexpr int APITCH = BK + 4;      // doubles per smem row of an (rows x BK) tile
+    static constexpr int A_TILE_MAX = 128 * APITCH;
+    static constexpr int B_TILE = (BN * APITCH > BK * BPITCH_NN) ? BN * APITCH : BK * BPITCH_NN;
+};
+template <int BK, int STAGES>
+constexpr int gemm_smem() { return STAGES * (KTile<BK>::A_TILE_MAX + KTile<BK>::B_TILE) * 8; }
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, int src_bytes)
 {
@@ -58,10 +58,11 @@ __device__ __forceinline__ void dmma(double &d0, double &d1, double a, double b)
 }
 
 // rows x BK tile of a row-major (k contiguous) matrix -> smem [rows][APITCH]
-template <int ROWS, bool VEC>
+template <int ROWS, bool VEC, int BK>
 __device__ __forceinline__ void load_tile_kmajor(double *sm, const double *g, long ld, int row0, int nrows,
                                                  int k0, int K)
 {
+    constexpr int APITCH = KTile<BK>::APITCH;
     if (VEC) {
         constexpr int CHUNKS = ROWS * (BK / 2);
 #pragma unroll
@@ -87,7 +88,7 @@ __device__ __forceinline__ void load_tile_kmajor(double *sm, const double *g, lo
 }
 
 // BK x BNT tile of a row-major (n contiguous) matrix -> smem [BK][BPITCH_NN]
-template <bool VEC, int BNT>
+template <bool VEC, int BNT, int BK>
 __device__ __forceinline__ void load_tile_nmajor(double *sm, const double *g, long ld, int k0, int K, int n0,
                                                  int N)
 {
@@ -124,7 +125,7 @@ struct GemmBatch {
     double *const *C;
 };
 
-template <bool TB, bool VEC, int MI, int NI, int WN>
+template <bool TB, bool VEC, int MI, int NI, int WN, int BK, int STAGES>
 __global__ void __launch_bounds__(256, 2)
 k_gemm_f64(const double *__restrict__ A, long lda, const double *__restrict__ B, long ldb,
            double *__restrict__ C, long ldc, int M, int N, int K, GemmBatch bt)
@@ -135,6 +136,7 @@ k_gemm_f64(const double *__restrict__ A, long lda, const double *__restrict__ B,
     constexpr int WM = 8 / WN;
     constexpr int BM = WM * 8 * MI, BNT = WN * 8 * NI;
     static_assert(BM <= 128 && BNT <= BN, "tile exceeds the shared-memory layout");
+    constexpr int APITCH = KTile<BK>::APITCH, B_TILE = KTile<BK>::B_TILE;
     constexpr int A_TILE = BM * APITCH;
     extern __shared__ __align__(16) double smem[];
     double *As = smem;
@@ -152,9 +154,9 @@ k_gemm_f64(const double *__restrict__ A, long lda, const double *__restrict__ B,
 
     const int KT = (K + BK - 1) / BK;
     auto load = [&](int kt, int stage) {
-        load_tile_kmajor<BM, VEC>(As + stage * A_TILE, A, lda, m0, M, kt * BK, K);
-        if (TB) load_tile_kmajor<BNT, VEC>(Bs + stage * B_TILE, B, ldb, n0, N, kt * BK, K);
-        else load_tile_nmajor<VEC, BNT>(Bs + stage * B_TILE, B, ldb, kt * BK, K, n0, N);
+        load_tile_kmajor<BM, VEC, BK>(As + stage * A_TILE, A, lda, m0, M, kt * BK, K);
+        if (TB) load_tile_kmajor<BNT, VEC, BK>(Bs + stage * B_TILE, B, ldb, n0, N, kt * BK, K);
+        else load_tile_nmajor<VEC, BNT, BK>(Bs + stage * B_TILE, B, ldb, kt * BK, K, n0, N);
     };
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
@@ -210,20 +212,34 @@ struct GemmShape {
 };
 static const GemmShape GEMM_SHAPES[] = {{128, 64}, {128, 56}, {128, 48}, {64, 64}, {32, 64}};
 
-template <bool TB, bool VEC, int MI, int NI, int WN>
-static int gemm_launch(const double *A, long lda, const double *B, long ldb, double *C, long ldc, int m, int n,
-                       int k, cudaStream_t st, GemmBatch bt = GemmBatch{nullptr, nullptr, nullptr}, int nbatch = 1)
+template <bool TB, bool VEC, int MI, int NI, int WN, int BK, int STAGES>
+static int gemm_launch_k(const double *A, long lda, const double *B, long ldb, double *C, long ldc, int m, int n,
+                         int k, cudaStream_t st, GemmBatch bt, int nbatch)
 {
-    auto kern = k_gemm_f64<TB, VEC, MI, NI, WN>;
+    auto kern = k_gemm_f64<TB, VEC, MI, NI, WN, BK, STAGES>;
+    constexpr int SMEM = gemm_smem<BK, STAGES>();
     static PerDeviceFlag attr;
     if (!attr.get()) {
-        PDE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
+        PDE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
         attr.get() = true;
     }
     constexpr int BM = (8 / WN) * 8 * MI, BNT = WN * 8 * NI;
     dim3 grid(ceil_div(n, BNT), ceil_div(m, BM), nbatch);
-    kern<<<grid, 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, m, n, k, bt);
+    kern<<<grid, 256, SMEM, st>>>(A, lda, B, ldb, C, ldc, m, n, k, bt);
     return after_launch("pde_gemm_f64");
+}
+
+template <bool TB, bool VEC, int MI, int NI, int WN>
+static int gemm_launch(const double *A, long lda, const double *B, long ldb, double *C, long ldc, int m, int n,
+                       int k, cudaStream_t st, GemmBatch bt = GemmBatch{nullptr, nullptr, nullptr}, int nbatch = 1)
+{
+    // two or more waves of CTAs (2 per SM): 32-deep K tiles, 2-stage ring; a single wave: 16-deep, 3 stages
+    constexpr int BM = (8 / WN) * 8 * MI, BNT = WN * 8 * NI;
+    const long tiles = (long)ceil_div(n, BNT) * ceil_div(m, BM) * nbatch;
+    static const int forced = getenv("PDE_GEMM_BK") ? atoi(getenv("PDE_GEMM_BK")) : 0;
+    const bool deep = forced ? forced == 32 : tiles >= 4L * sm_count();
+    if (deep) return gemm_launch_k<TB, VEC, MI, NI, WN, 32, 2>(A, lda, B, ldb, C, ldc, m, n, k, st, bt, nbatch);
+    return gemm_launch_k<TB, VEC, MI, NI, WN, 16, 3>(A, lda, B, ldb, C, ldc, m, n, k, st, bt, nbatch);
 }
 
 template <bool TB, bool VEC>
