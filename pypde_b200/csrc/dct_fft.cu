@@ -13,7 +13,9 @@
 // registers, one __syncthreads per pass, twiddles from an accurate host-built table);
 // its output stays in digit-reversed order and the split step reads it through a
 // permutation table, writing results straight to global memory:
-//   axis 1: a sequence is a contiguous row    -> fully coalesced loads/stores;
+//   axis 1: a sequence is a contiguous row    -> fully coalesced loads/stores; 16-byte aligned rows of the hot
+//           lengths go through k_dct_row_tma (dct_fft_t.cuh): persistent CTAs, the next row staged by the
+//           bulk-copy engine (cp.async.bulk + mbarrier) while the current one is transformed;
 //   axis 0: a sequence is a strided column    -> the CTA takes S adjacent columns, so every
 //           access is an S*8-byte segment (32 B sectors fully used for S = 4).
 // Zero padding (n_in < L), truncation (n_out < L) and the Chebyshev scale/sign/mass
